@@ -1,0 +1,259 @@
+/* sd_fusion.h -- C ABI of the B200-native SemanticDepth fusion path (libsd_fusion.so).
+ *
+ * The reference has no native code and no FFI: its fusion stage is Python that calls module-level
+ * functions of semantic_depth_lib/pcl.py (NumPy in, NumPy out) plus two Open3D calls.  The entry
+ * points below are what a binding for that path binds; each cites the reference interface it
+ * replaces (paths relative to /root/reference).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*;
+ *   - every pointer named d_* is DEVICE memory owned by the caller (no hidden allocation; scratch
+ *     comes from a caller-provided workspace, see sd_ws_*); h_* is HOST memory;
+ *   - clouds are structure-of-arrays: x[], y[], z[] fp32 and an optional int32 src[] carrying the
+ *     flat source index of each point (pixel index in the fused path, row index in the per-call ops);
+ *   - stable (order-preserving) compaction everywhere: output order == input order, exactly what
+ *     NumPy boolean / index-array selection produces;
+ *   - return value: SD_OK (0) or a negative SD_ERR_* code; sd_last_error() gives a message;
+ *   - all work is enqueued on `stream`; functions that return a count to the host synchronise that
+ *     stream once, sd_fuse_frames() never synchronises.
+ */
+#ifndef SD_FUSION_H
+#define SD_FUSION_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_ABI_VERSION 1
+
+enum {
+    SD_OK = 0,
+    SD_ERR_INVALID = -1,      /* bad argument (null pointer, size, axis, k ...) */
+    SD_ERR_CUDA = -2,         /* a CUDA runtime call failed; see sd_last_error() */
+    SD_ERR_WORKSPACE = -3,    /* workspace too small / not initialised */
+    SD_ERR_UNSUPPORTED = -4
+};
+
+/* Per-frame status bits of the fused path.  The reference signals these conditions with Python
+ * exceptions / None (pcl.py:107,232,303-304; semantic_depth.py:259); the facade maps them back. */
+enum {
+    SD_ST_EMPTY_ROAD = 1 << 0,
+    SD_ST_EMPTY_FENCE_LEFT = 1 << 1,
+    SD_ST_EMPTY_FENCE_RIGHT = 1 << 2,
+    SD_ST_MAD_ZERO = 1 << 3,
+    SD_ST_NO_SLAB_POINTS = 1 << 4,
+    SD_ST_SINGULAR_PLANES = 1 << 5,
+    SD_ST_EMPTY_FENCE = 1 << 6,
+    SD_ST_SINGULAR_FIT = 1 << 7
+};
+
+/* Per-stage point counts reported for every frame (the reference's cloud sizes after each call of
+ * semantic_depth.py:183-309, in call order). */
+enum {
+    SD_CNT_ROAD_GATHER = 0,   /* points3D[road_mask]            :183 */
+    SD_CNT_FENCE_GATHER,      /* points3D[fence_mask]           :186 */
+    SD_CNT_ROAD_Z,            /* remove_from_to                 :206 */
+    SD_CNT_ROAD_MAD_Y,        /* remove_noise_by_mad(1, 15)     :209 */
+    SD_CNT_ROAD_MAD_X,        /* remove_noise_by_mad(0, 2)      :212 */
+    SD_CNT_ROAD_PLANE,        /* remove_noise_by_fitting_plane  :215-219 */
+    SD_CNT_ROAD_SOR,          /* statistical_outlier_removal    :234-236 */
+    SD_CNT_ROAD_ROR,          /* radius_outlier_removal         :238-241 */
+    SD_CNT_ROAD_SLAB,         /* get_end_points_of_road slab    :254-255 */
+    SD_CNT_FENCE_MAD_Y,       /* :279 */
+    SD_CNT_FENCE_ABS_Z,       /* :283-284 */
+    SD_CNT_LEFT_SPLIT,        /* :286-287 */
+    SD_CNT_RIGHT_SPLIT,
+    SD_CNT_LEFT_MAD_X,        /* :291 */
+    SD_CNT_LEFT_PLANE,        /* :294-298 */
+    SD_CNT_RIGHT_MAD_X,       /* :302 */
+    SD_CNT_RIGHT_PLANE,       /* :305-309 */
+    SD_NUM_COUNTS
+};
+
+/* Camera of DepthFrame.compute_3D_points (semantic_depth.py:691-696): the four non-trivial entries
+ * of the reference's float32 Q matrix, and the fp32 disparity scale of semantic_depth.py:145. */
+typedef struct SdCamera {
+    float q03;             /* -cx  */
+    float q13;             /*  cy  */
+    float q23;             /* -f   */
+    float q32;             /* 1/b  */
+    float disparity_mult;  /* original image width (or 3800 in the sequence driver) */
+} SdCamera;
+
+/* The literals of FrameProcessor.process_frame's fusion section (semantic_depth.py:206-309). */
+typedef struct SdParams {
+    double prob_thr;          /* 0.5   :556,564 */
+    float road_z_to_meter;    /* 7.0   :206 */
+    float road_mad_y_thr;     /* 15.0  :209 */
+    float road_mad_x_thr;     /* 2.0   :212 */
+    float fence_mad_y_thr;    /* 5.0   :279 */
+    float fence_abs_z_thr;    /* 35.0  :283 */
+    float left_mad_x_thr;     /* 5.0   :291 */
+    float right_mad_x_thr;    /* 1.0   :302 */
+    int32_t sor_nb_neighbors; /* 10    :235 */
+    double road_plane_thr;    /* 5.0   :218 */
+    double fence_plane_thr;   /* 1.0   :297,308 */
+    double sor_std_ratio;     /* 0.5   :235 */
+    double ror_radius;        /* 0.5   :239 */
+    double slab_lo;           /* -((depth-0.02)+0.05), computed by the host as Python does (pcl.py:283) */
+    double slab_hi;           /* -((depth-0.02)-0.05) */
+    double depth;             /* 10.0  :736-738, used by the plane intersections :317-323 */
+    int32_t ror_nb_points;    /* 80    :239 */
+    int32_t use_sor;          /* 1 */
+    int32_t use_ror;          /* 1 */
+    int32_t approach_both;    /* 1 = rw and f2f, 0 = rw only (:273) */
+} SdParams;
+
+/* One frame's answers (what process_frame returns at :460 plus everything observable on the way). */
+typedef struct SdFrameResult {
+    double rw;                 /* |xL - xR|  :259 ; NaN when the slab is empty */
+    double f2f;                /* :324 ; NaN when unavailable */
+    double xl, xr;             /* min / max x of the slab (left / right end point, pcl.py:307-308) */
+    double left_pt[3];         /* road-plane x left-fence-plane at z = -depth (:317-319) */
+    double right_pt[3];        /* :321-323 */
+    double road_coeff[4];      /* Cx, Cy, Cz, C  (pcl.py:168) */
+    double left_coeff[4];      /* pcl.py:135 */
+    double right_coeff[4];
+    double sor_mean, sor_std, sor_thr;
+    float median[5];           /* medians of the five MAD calls: road y, road x, fence y, left x, right x */
+    float mad[5];
+    float fence_mean_x;        /* np.mean of extract_pcls (pcl.py:258) */
+    uint32_t status;           /* SD_ST_* */
+    int32_t counts[SD_NUM_COUNTS];
+    int32_t ransac_best[3];    /* best hypothesis index for road / left / right, -1 without RANSAC */
+} SdFrameResult;
+
+/* ---- library ------------------------------------------------------------------------------- */
+int sd_abi_version(void);
+const char* sd_last_error(void);
+/* Fills the reference's literals (semantic_depth.py:206-309) for the given depth (default 10). */
+void sd_default_params(SdParams* p, double depth);
+
+/* ---- workspace ------------------------------------------------------------------------------ */
+typedef struct SdWorkspace SdWorkspace;   /* host-side handle over caller-owned device memory */
+/* Bytes of device memory needed for `max_frames` frames of `height` x `width` pixels processed
+ * concurrently by sd_fuse_frames (also serves every per-call op on clouds of up to height*width
+ * points).  `max_hypotheses` > 0 reserves room for the RANSAC variant. */
+size_t sd_ws_bytes(int max_frames, int height, int width, int max_hypotheses);
+/* Carves `d_mem` (256-byte aligned, sd_ws_bytes() long), zeroes the control words and uploads the
+ * job descriptors.  Synchronises `stream` once. */
+int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int max_frames, int height, int width,
+                 int max_hypotheses, void* stream);
+void sd_ws_destroy(SdWorkspace* ws);
+
+/* ---- pixel stage ---------------------------------------------------------------------------- */
+/* Fused: labels (softmax > thr, semantic_depth.py:555-556,563-564) + post_processing blend
+ * (:656-664,676) + disparity scale (:145) + reprojectImageTo3D (:691-696) + raster-ordered gather
+ * of the road / fence points (:183-187) + the road z cut (:206).
+ *   d_logits [B][H*W][3] fp32, d_disp [B][2][H][W] fp32, d_lmask/d_rmask [W] fp64 ramps (:661-663).
+ * Optional outputs (may be NULL): d_labels [B][H*W] uint8 (bit0 road, bit1 fence);
+ *   d_points [B][H*W][3] fp32 = the full points3D array of :160; d_disp_pp [B][H*W] fp32 = :676.
+ * Cloud outputs live in the workspace (sd_fuse_frames) or in caller arrays (this call):
+ *   road_* receives the road points with z < -to_meter, fence_* all fence points, both with src =
+ *   flat pixel index; capacity H*W each, per frame stride H*W.  d_counts [B][3] int32 =
+ *   {road_gather, road_z, fence_gather}. */
+#define SD_PIX_RAW_DISPARITY 1   /* flags: d_disp[b][0] already is the blended, scaled disparity of :145 (skip blend and scale) */
+int sd_pixel_fuse(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
+                  int batch, int height, int width, const SdCamera* cam, double prob_thr, float road_z_to_meter, int flags,
+                  float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
+                  float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
+                  int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp,
+                  SdWorkspace* ws, void* stream);
+
+/* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
+/* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
+int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream);
+
+/* Predicate kinds of sd_filter(). */
+enum {
+    SD_PRED_LT = 0,        /* col < fa                                  remove_from_to      pcl.py:36 (fa = -to_meter) */
+    SD_PRED_ABS_LT = 1,    /* |col| < fa                                threshold_complete  pcl.py:247 */
+    SD_PRED_MAD = 2,       /* fl(fl(0.6745f*|col-f0|)/f1) < fa          remove_noise_by_mad pcl.py:63-67 (f0 = median, f1 = mad) */
+    SD_PRED_PLANE = 3,     /* |((d0*u + d1*v) - w) + d2| < da  (fp64)   remove_noise_by_fitting_plane pcl.py:130-131 */
+    SD_PRED_GT = 4,        /* col > fa                                  extract_pcls right  pcl.py:264 */
+    SD_PRED_SLAB = 5,      /* d0 < z < d1 (fp64) or fl32 bounds f0 < z < f1 when use_f32 */
+    SD_PRED_SOR = 6,       /* 0 < avg[i] < da                           Open3D RemoveStatisticalOutliers */
+    SD_PRED_ROR = 7        /* cnt[i] > ia                               Open3D RemoveRadiusOutliers */
+};
+typedef struct SdPredicate {
+    int32_t kind;
+    int32_t axis;          /* column the predicate reads (plane: the regressed axis) */
+    int32_t ia;
+    int32_t use_f32;
+    float fa, f0, f1;
+    float pad_;
+    double da, d0, d1, d2;
+    const void* d_aux;     /* SOR: const double* avg ; ROR: const int32_t* counts */
+} SdPredicate;
+
+/* Stable filter of one cloud.  Writes the surviving points to out_* (any may be NULL), out_src[i] =
+ * in_src[j] (or j itself when d_in_src is NULL, i.e. the kept row indices) and returns the number
+ * kept through h_n_out.  Synchronises the stream. */
+int sd_filter(const float* d_x, const float* d_y, const float* d_z, const int32_t* d_in_src, int n,
+              const SdPredicate* pred,
+              float* d_out_x, float* d_out_y, float* d_out_z, int32_t* d_out_src, int32_t* h_n_out,
+              SdWorkspace* ws, void* stream);
+
+/* Least-squares plane w = C0*u + C1*v + C2 of pcl.py:118-120 / 152-154 / 184-186 (axis = regressed
+ * coordinate).  h_coeff[3] = C0, C1, C2 (fp64).  Returns SD_OK and sets *h_singular when the normal
+ * equations are singular. */
+int sd_plane_fit(const float* d_x, const float* d_y, const float* d_z, int n, int axis,
+                 double* h_coeff, int32_t* h_singular, SdWorkspace* ws, void* stream);
+
+/* np.mean of an fp32 column with NumPy's pairwise fp32 summation order (pcl.py:258). */
+int sd_mean_f32(const float* d_col, int n, float* h_mean, SdWorkspace* ws, void* stream);
+
+/* min / max of x over the points with lo < z < hi and their count (pcl.py:283,307-308). */
+int sd_slab_minmax(const float* d_x, const float* d_z, int n, double lo, double hi, int use_f32,
+                   float* h_xmin, float* h_xmax, int32_t* h_count, SdWorkspace* ws, void* stream);
+
+/* Open3D RemoveStatisticalOutliers' per-point quantity (semantic_depth.py:234-235): mean fp64
+ * distance to the k nearest neighbours, self included.  d_avg [n] fp64.  Also returns the cloud
+ * mean / Bessel std / threshold through h_stats[3] when not NULL. */
+int sd_knn_mean_distance(const float* d_x, const float* d_y, const float* d_z, int n, int k, double std_ratio,
+                         double* d_avg, double* h_stats, SdWorkspace* ws, void* stream);
+
+/* Open3D RemoveRadiusOutliers' per-point quantity (semantic_depth.py:238-239): number of points
+ * within `radius` (self included), saturated at `cap`+1 when cap >= 0 (only count > cap matters). */
+int sd_radius_count(const float* d_x, const float* d_y, const float* d_z, int n, double radius, int cap,
+                    int32_t* d_counts, SdWorkspace* ws, void* stream);
+
+/* RANSAC scoring (north_star row 8-R): inlier count of each hypothesis plane through the points
+ * d_triplets[k][3]; d_hyp_counts [K] int32; h_best = arg max (lowest index on ties). */
+int sd_ransac_score(const float* d_x, const float* d_y, const float* d_z, int n, int axis, double threshold,
+                    const int32_t* d_triplets, int n_hyp, int32_t* d_hyp_counts, int32_t* h_best,
+                    double* h_best_coeff, SdWorkspace* ws, void* stream);
+
+/* ---- the fused per-frame path ---------------------------------------------------------------- */
+/* Everything between the two networks' raw outputs and (rw, f2f) for `batch` frames, enqueued on
+ * `stream` without any host synchronisation (CUDA-graph capturable).  d_results [batch].
+ * d_hyp_* : optional RANSAC triplets per chain ([batch][n_hyp][3] each, may be NULL = reference
+ * behaviour, all-points least squares). */
+int sd_fuse_frames(const float* d_logits, const float* d_disp, int batch, int height, int width,
+                   const SdCamera* cam, const SdParams* params,
+                   const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
+                   SdFrameResult* d_results, SdWorkspace* ws, void* stream);
+
+/* Same through HOST buffers (the reference-facing call: NumPy arrays in, results out): copies the
+ * inputs host->device, runs sd_fuse_frames and copies the results back, all on `stream`, then
+ * synchronises.  d_logits_stage / d_disp_stage are caller-owned device staging buffers. */
+int sd_fuse_frames_host(const float* h_logits, const float* h_disp, int batch, int height, int width,
+                        const SdCamera* cam, const SdParams* params,
+                        float* d_logits_stage, float* d_disp_stage, SdFrameResult* d_results,
+                        SdFrameResult* h_results, SdWorkspace* ws, void* stream);
+
+/* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):
+ * which = 0 road (after ROR), 1 left fence (after plane filter), 2 right fence. */
+int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,
+                const int32_t** d_src, const int32_t** d_n);
+/* Device pointers of a frame's intermediate per-stage source-index lists for parity tests:
+ * stage = SD_CNT_* ; only stages that materialise a cloud are available (returns SD_ERR_UNSUPPORTED otherwise). */
+int sd_ws_stage_src(SdWorkspace* ws, int frame, int stage, const int32_t** d_src);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD_FUSION_H */

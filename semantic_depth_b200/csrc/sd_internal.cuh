@@ -1,0 +1,220 @@
+// Internal job descriptors, workspace layout and launcher prototypes.  Every cloud kernel is
+// "batched over jobs": blockIdx.y selects a job descriptor (one cloud of one frame), all sizes are
+// read from device memory, so a whole batch of frames runs without any host round trip.
+#pragma once
+#include "sd_common.cuh"
+
+namespace sd {
+
+constexpr int kSelBits0 = 11, kSelBits1 = 11, kSelBits2 = 10;   // radix-select digit widths (32 bits)
+constexpr int kSelBins = 2048;
+constexpr int kCompactThreads = 512;
+constexpr int kCompactItems = 8;
+constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 4096 points per tile
+constexpr int kScanTile = 4096;                                 // cell-count scan tile
+constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job
+constexpr int kPlaneSums = 9;
+constexpr int kMaxKnnK = 64;
+
+// ---- device-side per-frame scalars --------------------------------------------------------------
+struct FrameState {
+    int32_t n[SD_NUM_COUNTS];   // stage counts; also the n_in/n_out cells the jobs point to
+    int32_t n_sor_alive;
+    int32_t slab_count;
+    uint32_t slab_keys[2];      // ordered keys of min / max x in the slab
+    uint32_t status;
+    float med[5], mad[5];       // road y, road x, fence y, left x, right x
+    float fence_mean;
+    float pad_;
+    double coeff[3][3];         // road / left / right plane: C0, C1, C2 (regression form)
+    double sor_stats[3];        // mean, std, threshold
+    int32_t ransac_best[3];
+    int32_t pad2_;
+};
+
+// ---- radix select ----------------------------------------------------------------------------------
+struct SelState {
+    uint32_t prefix[2];         // key bits resolved so far for the lower / upper middle rank
+    uint32_t rank[2];           // remaining rank inside the prefix bucket
+    uint32_t nan_count;
+    uint32_t ticket;
+    uint32_t pad_[2];
+    uint32_t hist[2][kSelBins];
+};
+struct SelJob {
+    const float* col;
+    const int32_t* n;
+    const float* center;        // nullptr: keys are col[i]; else keys are |col[i] - *center|
+    SelState* st;
+    float* out;                 // the median
+    uint32_t* status;           // optional status word
+    uint32_t zero_bit;          // OR'ed into *status when n > 0 and !(median > 0)  (MAD == 0 / NaN)
+    uint32_t pad_;
+};
+
+// ---- stable compaction -------------------------------------------------------------------------------
+struct PredDev {
+    int32_t kind, axis, ia, use_f32;
+    float fa, f0, f1, pad_;
+    double da, d0, d1, d2;
+    const void* aux;            // SOR: const double* avg ; ROR: const int32_t* counts
+    const void* aux2;           // SOR+ROR fused: const int32_t* counts
+    const float* p_f0;          // device-resident overrides (fused path): median / mean
+    const float* p_f1;          // mad
+    const double* p_d;          // plane C0,C1,C2 ; SOR: threshold at p_d[0]
+};
+constexpr int SD_PRED_SORROR = 100;   // internal: 0 < avg < thr (if p_d) && cnt > ia (if aux2)
+
+struct CompactJob {
+    const float* x; const float* y; const float* z; const int32_t* src; const int32_t* n_in;
+    float* ox; float* oy; float* oz; int32_t* osrc; int32_t* n_out;
+    PredDev pred;
+    unsigned long long* status; // look-back words, max_tiles long
+    ScanCtl* ctl;
+    uint32_t* frame_status;     // optional: OR `empty_bit` when the output is empty
+    uint32_t empty_bit;
+    int32_t max_tiles;
+};
+
+// ---- plane fit -----------------------------------------------------------------------------------------
+struct PlaneJob {
+    const float* x; const float* y; const float* z; const int32_t* n;
+    int32_t axis;               // regressed coordinate (pcl.py axis argument)
+    int32_t use_inliers;        // RANSAC refit: only points with |res(hyp)| < thr contribute
+    const double* hyp;          // C0,C1,C2 of the best hypothesis (device)
+    double thr;
+    double* partials;           // [kPlaneBlocks][kPlaneSums]
+    uint32_t* ticket;
+    double* coeff;              // out: C0, C1, C2
+    uint32_t* status;           // optional
+    uint32_t empty_bit;         // OR'ed when n == 0
+    uint32_t pad_;
+};
+
+// ---- NumPy pairwise fp32 mean ----------------------------------------------------------------------------
+struct MeanJob {
+    const float* col; const int32_t* n; float* out;
+};
+
+// ---- slab min/max ---------------------------------------------------------------------------------------
+struct SlabJob {
+    const float* x; const float* z; const int32_t* n;
+    double lo, hi; float lo32, hi32; int32_t use_f32; int32_t pad_;
+    uint32_t* keys;             // [2] min / max ordered keys (reset to 0xffffffff / 0 by the consumer)
+    int32_t* count;
+};
+
+// ---- uniform grid / kNN ------------------------------------------------------------------------------------
+struct GridState {
+    uint32_t bbox[6];           // ordered keys: min x,y,z then max x,y,z  (reset by the last bbox block)
+    uint32_t ticket;
+    int32_t ncells;
+    int32_t a0, a1, a2;         // a0 = fast grid axis, a1 = slow grid axis, a2 = collapsed axis
+    int32_t d0, d1;             // cells along a0 / a1
+    int32_t n;                  // snapshot of the cloud size
+    double o0, o1;              // grid origin along a0 / a1
+    double cell, inv_cell;
+    double ext2;                // extent of the collapsed axis (for the 2D-inside shortcut)
+};
+struct KnnJob {
+    const float* x; const float* y; const float* z; const int32_t* n;
+    GridState* gs;
+    int32_t* cell_count;        // [cell_cap + 1], all zero between launches
+    int32_t* cell_start;        // [cell_cap + 1]
+    int32_t* cell_of;           // [cap] cell of each point (input order)
+    float* sx; float* sy; float* sz; int32_t* sorig;   // cell-sorted copies
+    double* avg;                // [cap] mean kNN distance, by ORIGINAL index
+    double* savg;               // [cap] same, by sorted index
+    int32_t* cnt;               // [cap] radius counts, by original index
+    unsigned long long* scan_status; ScanCtl* scan_ctl;
+    double* stats;              // mean, std, thr
+    int32_t* n_alive;
+    int32_t cell_cap;
+    int32_t k;
+    double std_ratio;
+    double radius;
+    int32_t nb_points;
+    int32_t use_sor;            // 0: every point is alive for the radius count
+    int32_t count_cap;          // saturate radius counts at count_cap + 1 (-1: exact counts)
+    int32_t pad_;
+    double* part;               // [kKnnMaxBlocks][3] per-CTA partial sums of the cloud statistics
+    double cell_scale;          // cell edge = cell_scale * sqrt(area / n)
+};
+constexpr int kKnnMaxBlocks = 148 * 16;
+
+// ---- RANSAC ----------------------------------------------------------------------------------------------
+struct RansacJob {
+    const float* x; const float* y; const float* z; const int32_t* n;
+    const int32_t* triplets;    // [n_hyp][3]
+    double* hyp_coeff;          // [n_hyp][4]: C0, C1, C2, valid
+    int32_t* hyp_counts;        // [n_hyp]
+    int32_t* best;              // out
+    double* best_coeff;         // out: C0,C1,C2
+    int32_t axis; int32_t n_hyp;
+    double thr;
+};
+
+// ---- finalize ----------------------------------------------------------------------------------------------
+struct FinalJob {
+    FrameState* fs;
+    SdFrameResult* out;
+};
+
+}  // namespace sd
+
+// ---- host-side workspace ------------------------------------------------------------------------------------
+struct SdCloudBuf { float* x; float* y; float* z; int32_t* src; };
+
+struct SdWorkspace {
+    char* base; size_t bytes;
+    int max_frames, height, width, cap, max_tiles, cell_cap, max_hyp;
+    // per-frame arrays (index = frame)
+    sd::FrameState* fs;                  // [F]
+    SdCloudBuf road[2], fence[2], left[2], right[2];   // each buffer: F * cap elements per array
+    // select / scan / plane scratch per (frame, chain) ; chain: 0 road, 1 fence, 2 left, 3 right
+    sd::SelState* sel;                   // [F][4]
+    unsigned long long* cstatus;         // [F][4][max_tiles]
+    sd::ScanCtl* cctl;                   // [F][4]
+    double* partials;                    // [F][4][kPlaneBlocks*kPlaneSums]
+    uint32_t* ptick;                     // [F][4]
+    // pixel pass
+    unsigned long long* pstatus;         // [F][pix_tiles]
+    sd::ScanCtl* pctl;                   // [F]
+    int pix_tiles;
+    double* lmask; double* rmask;        // [width] blend ramps (uploaded at create)
+    // grid / knn per frame
+    sd::GridState* gs;                   // [F]
+    int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
+    float* sx; float* sy; float* sz; int32_t* sorig;
+    double* avg; double* savg; int32_t* cnt; double* knn_part;
+    unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
+    // ransac per (frame, chain 0..2)
+    double* hyp_coeff; int32_t* hyp_counts; double* best_coeff;
+    // job descriptor arenas (device) + small host-visible scratch
+    char* jobs; size_t jobs_bytes; size_t jobs_used;
+    char* scratch; size_t scratch_bytes;     // device scratch for per-call ops (results, descriptors)
+    void* h_pinned; size_t h_pinned_bytes;   // pinned host mirror for small readbacks
+    // prebuilt descriptor arrays for the fused path (device pointers)
+    bool fused_ready;
+    int fused_batch;
+    SdParams fused_params;
+};
+
+// launchers (each returns SD_OK / SD_ERR_*); jobs are DEVICE pointers
+int sd_launch_select_median(const sd::SelJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_compact(const sd::CompactJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_plane(const sd::PlaneJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, cudaStream_t st);
+int sd_launch_slab(const sd::SlabJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
+int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, cudaStream_t st);
+int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
+int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
+int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
+                    int batch, int height, int width, SdCamera cam, double prob_thr, float road_z, int flags,
+                    SdCloudBuf road, SdCloudBuf fence, int cap_stride,
+                    int32_t* d_cnt_road_gather, int32_t* d_cnt_road_z, int32_t* d_cnt_fence, int cnt_stride,
+                    uint8_t* d_labels, float* d_points, float* d_disp_pp,
+                    unsigned long long* status, sd::ScanCtl* ctl, int pix_tiles, cudaStream_t st);

@@ -1,0 +1,86 @@
+"""Frame-level entry points of the facade: the pixel stage pieces and the fused path.
+
+These are the inline NumPy / OpenCV steps of ``FrameProcessor.process_frame`` and its helpers
+(/root/reference/semantic_depth.py:550-564, 656-664, 686-697, 183-324) as single calls.  NumPy in ->
+NumPy out, CUDA tensors in -> CUDA tensors out.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import FusionEngine
+from .params import FusionParams, Intrinsics
+
+_frame_engines: dict = {}
+
+
+def frame_engine(height: int, width: int, max_frames: int = 1, device="cuda:0", max_hypotheses: int = 0) -> FusionEngine:
+    key = (height, width, str(device))
+    eng = _frame_engines.get(key)
+    if eng is None or eng.max_frames < max_frames or eng.max_hyp < max_hypotheses:
+        if eng is not None:
+            eng.close()
+        eng = FusionEngine(height, width, max_frames=max(max_frames, 1), max_hypotheses=max_hypotheses, device=device)
+        _frame_engines[key] = eng
+    return eng
+
+
+def _dev(x, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.to(device="cuda", dtype=dtype).contiguous(), True
+    return torch.from_numpy(np.ascontiguousarray(x)).to(device="cuda", dtype=dtype).contiguous(), False
+
+
+def _back(t, was_torch):
+    return t if was_torch else t.cpu().numpy()
+
+
+def labels_from_logits(logits, shape, prob_thr: float = 0.5):
+    """(road_mask, fence_mask) bool [H,W]: ``softmax(logits)[:, c] > prob_thr`` for c = 0, 1
+    (semantic_depth.py:555-556,563-564), decided as an fp64 softmax would."""
+    h, w = shape
+    lg, was_torch = _dev(logits)
+    lg = lg.reshape(1, h * w, 3)
+    eng = frame_engine(h, w)
+    disp = torch.ones((1, 2, h, w), dtype=torch.float32, device=lg.device)
+    out = eng.pixel_stage(lg, disp, Intrinsics.synthetic(w), prob_thr=prob_thr)
+    lab = out["labels"].reshape(h, w)
+    return _back((lab & 1) != 0, was_torch), _back((lab & 2) != 0, was_torch)
+
+
+def post_process_disparity(disp):
+    """DepthFrame.post_processing + the fp32 cast (semantic_depth.py:656-664,676): [2,H,W] -> [H,W]."""
+    d, was_torch = _dev(disp)
+    _, h, w = d.shape
+    eng = frame_engine(h, w)
+    lg = torch.zeros((1, h * w, 3), dtype=torch.float32, device=d.device)
+    out = eng.pixel_stage(lg, d.reshape(1, 2, h, w), Intrinsics.synthetic(w))
+    return _back(out["disp_pp"].reshape(h, w), was_torch)
+
+
+def reproject_to_3d(disparity, intr: Intrinsics):
+    """DepthFrame.compute_3D_points (semantic_depth.py:686-697): cv2.reprojectImageTo3D(disp, Q) for the
+    fp32 pixel disparity of :145 -> [H,W,3] fp32."""
+    d, was_torch = _dev(disparity)
+    h, w = d.shape
+    eng = frame_engine(h, w)
+    lg = torch.zeros((1, h * w, 3), dtype=torch.float32, device=d.device)
+    pair = torch.stack([d, d], dim=0).reshape(1, 2, h, w).contiguous()
+    out = eng.pixel_stage(lg, pair, intr, raw_disparity=True)
+    return _back(out["points"].reshape(h, w, 3), was_torch)
+
+
+def fuse_frames(logits, disp, intrinsics: Intrinsics, params: FusionParams | None = None, ransac_hypotheses=None):
+    """The fusion section of process_frame (semantic_depth.py:183-324) for a batch of frames.
+
+    ``logits`` [B,H*W,3], ``disp`` [B,2,H,W] (NumPy / CPU tensors -> host entry point with H2D copies;
+    CUDA tensors are consumed in place).  Returns a ``FusionResult`` (rw[B], f2f[B], status[B], xl/xr,
+    plane coefficients, per-stage counts)."""
+    b, _, h, w = disp.shape
+    n_hyp = 0
+    if ransac_hypotheses:
+        n_hyp = max(int(v.shape[1]) for v in ransac_hypotheses.values() if v is not None)
+    dev = logits.device if isinstance(logits, torch.Tensor) and logits.is_cuda else "cuda:0"
+    eng = frame_engine(h, w, max_frames=b, device=dev, max_hypotheses=n_hyp)
+    return eng.fuse_frames(logits, disp, intrinsics, params, ransac_hypotheses)

@@ -85,7 +85,7 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     __shared__ int s_tile;
     __shared__ unsigned long long s_excl;
 
-    const CompactJob& J = jobs[blockIdx.y];
+    const CompactJob J = jobs[blockIdx.y];
     const int n = *J.n_in;
     const int tid = threadIdx.x;
     const int ntiles = ceil_div(n, kCompactTile);
@@ -96,6 +96,7 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     const bool need_z = (P.kind == SD_PRED_PLANE) || (J.oz != nullptr) || (P.axis == 2 && P.kind <= SD_PRED_GT) ||
                         (P.kind == SD_PRED_SLAB);
 
+    const bool vec_ok = ((((uintptr_t)X) | ((uintptr_t)Y) | ((uintptr_t)Z)) & 15) == 0;   // 128-bit loads need alignment
     while (true) {
         if (tid == 0) s_tile = (int)atomicAdd(&J.ctl->ticket, 1u);
         __syncthreads();
@@ -105,7 +106,7 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
         float x[kCompactItems], y[kCompactItems], z[kCompactItems];
         bool keep[kCompactItems];
         int cnt = 0;
-        if (base + kCompactItems <= n) {
+        if (vec_ok && base + kCompactItems <= n) {
 #pragma unroll
             for (int q = 0; q < kCompactItems / 4; ++q) {
                 float4 a = need_x ? __ldg(reinterpret_cast<const float4*>(X + base) + q) : make_float4(0, 0, 0, 0);
@@ -154,7 +155,7 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     }
     if (scan_finish(J.ctl, J.status, max(ntiles, 0), gridDim.x)) {
         if (tid == 0) {
-            int nout = (n > 0) ? *J.n_out : 0;
+            int nout = (n > 0 && J.n_out) ? __ldcg(J.n_out) : 0;
             if (n <= 0 && J.n_out) *J.n_out = 0;
             if (J.frame_status && J.empty_bit && nout == 0) atomicOr(J.frame_status, J.empty_bit);
         }

@@ -115,6 +115,7 @@ struct GridState {
     double o0, o1;              // grid origin along a0 / a1
     double cell, inv_cell;
     double ext2;                // extent of the collapsed axis (for the 2D-inside shortcut)
+    unsigned long long acc[3][2];  // exact 128-bit fixed-point sums of avg, avg^2 (lo, hi) and the count of avg > 0
 };
 struct KnnJob {
     const float* x; const float* y; const float* z; const int32_t* n;

@@ -168,6 +168,47 @@ __device__ __forceinline__ GridRt load_grid(const GridState* gs) {
     return g;
 }
 
+// ---- exact, order-independent accumulation of the cloud statistics ------------------------------------
+// The per-point means are bit-exact, but their summation order would depend on the (atomic) order of
+// points inside a cell.  Summing 2^-70 fixed-point images of the values in 128-bit integers is exact
+// and associative, so the cloud mean / std are deterministic run to run (and closer to the real sum
+// than any fp64 summation order).
+struct U128 { unsigned long long lo, hi; };
+__device__ __forceinline__ U128 to_fixed70(double v) {      // floor(v * 2^70) for finite v > 0, else 0
+    U128 r{0ull, 0ull};
+    if (!(v > 0.0)) return r;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const int e = (int)((bits >> 52) & 0x7ffull);
+    if (e == 0 || e == 0x7ff) return r;
+    const unsigned long long m = (bits & 0xfffffffffffffull) | (1ull << 52);
+    int sh = e - 1075 + 70;                                  // v = m * 2^(e-1075)
+    if (sh > 74) sh = 74;                                    // saturate (|v| >= 2^57 never happens for metres)
+    if (sh >= 64) { r.hi = m << (sh - 64); }
+    else if (sh > 0) { r.lo = m << sh; r.hi = m >> (64 - sh); }
+    else if (sh == 0) { r.lo = m; }
+    else if (sh > -64) { r.lo = m >> (-sh); }
+    return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+    U128 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull); return r;
+}
+__device__ __forceinline__ U128 warp_sum128(U128 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        U128 t; t.lo = __shfl_xor_sync(SD_FULL, v.lo, o); t.hi = __shfl_xor_sync(SD_FULL, v.hi, o);
+        v = add128(v, t);
+    }
+    return v;
+}
+__device__ __forceinline__ void atomic_add128(unsigned long long* acc, U128 v) {
+    const unsigned long long old = atomicAdd(&acc[0], v.lo);
+    const unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
+    if (v.hi | carry) atomicAdd(&acc[1], v.hi + carry);
+}
+__device__ __forceinline__ double fixed70_to_double(unsigned long long lo, unsigned long long hi) {
+    return ((double)hi * 18446744073709551616.0 + (double)lo) * 8.470329472543003e-22;   // 2^-70
+}
+
 template <int KCAP>
 struct Best {
     double d[KCAP];      // descending: d[0] is the current k-th smallest (the worst kept)
@@ -214,13 +255,13 @@ __device__ __forceinline__ void scan_range(const KnnJob& J, int s, int e, float 
 template <int KCAP>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const KnnJob* __restrict__ jobs) {
-    __shared__ double s_red[3][kKnnThreads / 32];
     __shared__ int s_last;
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const int keff = min(J.k, g.n);
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double acc_sum = 0.0, acc_sq = 0.0, acc_pos = 0.0;
+    U128 acc_sum{0ull, 0ull}, acc_sq{0ull, 0ull};
+    unsigned long long acc_pos = 0ull;
 
     for (int i = blockIdx.x * kKnnThreads + threadIdx.x; i < g.n; i += gridDim.x * kKnnThreads) {
         const float qx = __ldg(J.sx + i), qy = __ldg(J.sy + i), qz = __ldg(J.sz + i);
@@ -253,18 +294,16 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
         const double avg = (keff > 0) ? best.sum_sqrt_ascending() / (double)keff : -1.0;
         J.avg[__ldg(J.sorig + i)] = avg;
         J.savg[i] = avg;
-        if (avg > 0.0) { acc_sum += avg; acc_sq += avg * avg; acc_pos += 1.0; }
+        if (avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
     }
 
-    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): per-CTA partials
-    acc_sum = warp_sum(acc_sum); acc_sq = warp_sum(acc_sq); acc_pos = warp_sum(acc_pos);
-    if (lane_id() == 0) { s_red[0][warp_id()] = acc_sum; s_red[1][warp_id()] = acc_sq; s_red[2][warp_id()] = acc_pos; }
-    __syncthreads();
-    double* part = J.part;
-    if (threadIdx.x < 3) {
-        double t = 0.0;
-        for (int w = 0; w < kKnnThreads / 32; ++w) t += s_red[threadIdx.x][w];
-        part[blockIdx.x * 3 + threadIdx.x] = t;
+    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums
+    acc_sum = warp_sum128(acc_sum); acc_sq = warp_sum128(acc_sq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc_pos += __shfl_xor_sync(SD_FULL, acc_pos, o);
+    if (lane_id() == 0 && acc_pos) {
+        atomic_add128(J.gs->acc[0], acc_sum); atomic_add128(J.gs->acc[1], acc_sq);
+        atomicAdd(&J.gs->acc[2][0], acc_pos);
     }
     __threadfence();
     __syncthreads();
@@ -273,10 +312,11 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
     if (!s_last) return;
     __threadfence();
     if (threadIdx.x == 0) {
-        double S = 0.0, Q = 0.0, Pn = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) {
-            S += __ldcg(&part[b * 3 + 0]); Q += __ldcg(&part[b * 3 + 1]); Pn += __ldcg(&part[b * 3 + 2]);
-        }
+        GridState* gs = J.gs;
+        const double S = fixed70_to_double(__ldcg(&gs->acc[0][0]), __ldcg(&gs->acc[0][1]));
+        const double Q = fixed70_to_double(__ldcg(&gs->acc[1][0]), __ldcg(&gs->acc[1][1]));
+        const double Pn = (double)__ldcg(&gs->acc[2][0]);
+        gs->acc[0][0] = gs->acc[0][1] = gs->acc[1][0] = gs->acc[1][1] = gs->acc[2][0] = gs->acc[2][1] = 0ull;
         const double n = (double)g.n;
         const double mean = (g.n > 0) ? S / n : 0.0;
         // sum over avg>0 of (avg-mean)^2 = Q - 2*mean*S + Pn*mean^2

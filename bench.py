@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Benchmark of the fusion hot path: frames/s at 1024x2048 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the fused path over one batch of 5 synthetic Cityscapes-shaped frames
+(BASELINE.json configs[1], "Munich-test-set-shaped batch of 5 frames at 1024x2048").  Ranks are
+independent (frame-parallel, weak scaling, no collective on the data path).  One JSON line on rank 0.
+
+  value     frames/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       frames/s through the host-facing API: pinned host inputs, H2D + fused path + D2H of the
+            answers inside the timed region
+  roofline  the pixel-stage kernel (the HBM-bound kernel of the path): algorithmic bytes per launch /
+            its mean device time measured with CUDA events inside the timed region, vs the measured
+            HBM peak of MEASURED_PEAKS.json; roofline_path = the whole path's SURVEY 8d B_alg figure
+  cpu_baseline / --impl reference   the oracle port of the reference's CPU path on the host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fusion_frames_per_sec_1024x2048"
+UNIT = "frames/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--height", type=int, default=1024)
+    ap.add_argument("--width", type=int, default=2048)
+    ap.add_argument("--frames", type=int, default=5, help="frames per batch (= per step)")
+    ap.add_argument("--slots", type=int, default=3, help="batches in flight per GPU")
+    ap.add_argument("--batches", type=int, default=6, help="distinct input batches resident in HBM (cycled)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 40)")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    return ap.parse_args()
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+def workload_name(a):
+    return f"batch of {a.frames} synthetic Cityscapes-shaped frames at {a.height}x{a.width} (BASELINE.json configs[1])"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (NVML, in-process)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz, self.ok = index, [], set(), False, None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the oracle port of the reference's CPU path on the host cores
+# ------------------------------------------------------------------------------------------------
+def run_reference(a):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    from oracle.cpu_baseline import CpuBaseline
+    cb = CpuBaseline(a.height, a.width, procs=a.cpu_procs or None)
+    t_first = None
+    warm = 0
+    # CPU code has nothing to warm but the process pool; one warm-up step also calibrates the budget
+    for _ in range(min(a.warmup, 1)):
+        t_first, _, _ = cb.step()
+        warm += 1
+    est = t_first if t_first else 25.0
+    steps = max(1, min(a.steps, int((a.ref_budget_s - (t_first or 0.0)) // max(est, 1e-3))))
+    total, frames = 0.0, 0
+    for _ in range(steps):
+        wall, n, _ = cb.step()
+        total += wall
+        frames += n
+    cb.close()
+    value = frames / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "steps_requested": a.steps, "warmup": warm, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (NumPy)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "height": a.height, "width": a.width, "frames_per_step": cb.procs,
+                   "note": "CPU arm: each step = one full-resolution frame per worker process (bounded sample of the "
+                           "5-frame batch workload); executed steps are capped by --ref-budget-s"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cb.cores_used, "kind": "port", "sample": cb.describe()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "host_cores": os.cpu_count(),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def b_alg_bytes(counts: dict, hw: int) -> float:
+    """20*H*W + 12*(N_R0+N_F0) + 12*sum_stages(N_in+N_out) + 12*N_slab_in."""
+    c = counts
+    stages = [("road_gather", "road_z"), ("road_z", "road_mad_y"), ("road_mad_y", "road_mad_x"), ("road_mad_x", "road_plane"),
+              ("road_plane", "road_sor"), ("road_sor", "road_ror"),
+              ("fence_gather", "fence_mad_y"), ("fence_mad_y", "fence_abs_z"),
+              ("left_split", "left_mad_x"), ("left_mad_x", "left_plane"), ("right_split", "right_mad_x"),
+              ("right_mad_x", "right_plane")]
+    total = 20.0 * hw + 12.0 * (c["road_gather"] + c["fence_gather"])
+    total += 12.0 * sum(c[i] + c[o] for i, o in stages)
+    total += 12.0 * (c["fence_abs_z"] + c["left_split"] + c["right_split"])      # extract_pcls: 1 in, 2 out
+    total += 12.0 * c["road_ror"]                                                 # slab scan input
+    return total
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from semantic_depth_b200 import scene
+    from semantic_depth_b200.params import FusionParams, Intrinsics
+    from semantic_depth_b200.stream import FramePipeline
+
+    rank, local_rank, world = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    H, W, B, HW = a.height, a.width, a.frames, a.height * a.width
+    P = FusionParams()
+    intr = Intrinsics.synthetic(W)
+
+    # ---- synthetic inputs: `batches` distinct batches, pinned on the host and resident in HBM
+    nb = max(a.batches, a.slots)
+    h_logits = [torch.empty((B, HW, 3), dtype=torch.float32).pin_memory() for _ in range(nb)]
+    h_disp = [torch.empty((B, 2, H, W), dtype=torch.float32).pin_memory() for _ in range(nb)]
+    for i in range(nb):
+        lg, dp, _ = scene.make_batch(B, H, W, first_seed=rank * 100000 + i * B, intr=intr)
+        h_logits[i].copy_(torch.from_numpy(lg))
+        h_disp[i].copy_(torch.from_numpy(dp))
+    d_logits = [t.to(dev) for t in h_logits]
+    d_disp = [t.to(dev) for t in h_disp]
+    input_bytes = nb * B * HW * 20
+
+    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=True)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- expected answers (also builds job tables and captures the graphs): one pass over every
+    #      (slot, batch) pair that the timed loop will use
+    expected = {}
+    for b in range(nb):
+        for tag, res in pipe.warm_device(d_logits[b], d_disp[b], intr, tag=b):
+            expected.setdefault(tag, res)
+    pipe.pixel_ms.clear(); pipe.total_ms.clear()
+
+    def run_device_steps(n, check):
+        bad = 0
+        for i in range(n):
+            fin = pipe.submit_device(d_logits[i % nb], d_disp[i % nb], intr, tag=i % nb)
+            if fin and check:
+                bad += fin[1].raw.tobytes() != expected[fin[0]].raw.tobytes()
+        for tag, res in pipe.drain():
+            if check:
+                bad += res.raw.tobytes() != expected[tag].raw.tobytes()
+        return bad
+
+    # ---- warm-up, then the timed region (device-resident inputs)
+    run_device_steps(a.warmup, False)
+    pipe.pixel_ms.clear(); pipe.total_ms.clear()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
+    t0.record(main)
+    for s in pipe.slots:
+        s.stream.wait_event(t0)
+    wall0 = time.perf_counter()
+    mismatches = run_device_steps(a.steps, True)
+    for s in pipe.slots:
+        main.wait_stream(s.stream)
+    t1.record(main)
+    barrier()
+    wall = time.perf_counter() - wall0
+    elapsed_ms = t0.elapsed_time(t1)
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+    pixel_ms = list(pipe.pixel_ms)
+    total_ms = list(pipe.total_ms)
+
+    # ---- end to end: pinned host inputs -> H2D -> fused path -> D2H of the answers, pipelined over the slots
+    e2e = None
+    if not a.skip_e2e:
+        ke = a.e2e_steps or min(a.steps, 40)
+        for i in range(min(3, ke)):
+            pipe.submit_host(h_logits[i % nb], h_disp[i % nb], intr, tag=i % nb)
+        pipe.drain()
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for s in pipe.slots:
+            s.stream.wait_event(e0)
+        bad = 0
+        for i in range(ke):
+            fin = pipe.submit_host(h_logits[i % nb], h_disp[i % nb], intr, tag=i % nb)
+            if fin:
+                bad += fin[1].raw.tobytes() != expected[fin[0]].raw.tobytes()
+        for tag, res in pipe.drain():
+            bad += res.raw.tobytes() != expected[tag].raw.tobytes()
+        for s in pipe.slots:
+            main.wait_stream(s.stream)
+        e1.record(main)
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+        mismatches += bad
+        e2e = (ke, e2e_ms)
+
+    # ---- reduce over ranks (max time)
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    elapsed_ms = max_over_ranks(elapsed_ms)
+    if e2e:
+        e2e = (e2e[0], max_over_ranks(e2e[1]))
+    mism = int(max_over_ranks(float(mismatches)))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        counts0 = expected[0].counts(0)
+        # pixel-stage kernel: algorithmic bytes per launch = sum over the batch of 20*HW + 12*(N_R0+N_F0)
+        per_batch_pixel_bytes = []
+        per_batch_alg = []
+        for b in range(nb):
+            r = expected[b]
+            pb = sum(20.0 * HW + 12.0 * (r.counts(f)["road_gather"] + r.counts(f)["fence_gather"]) for f in range(B))
+            per_batch_pixel_bytes.append(pb)
+            per_batch_alg.append(sum(b_alg_bytes(r.counts(f), HW) for f in range(B)))
+        pix_bytes = float(np.mean(per_batch_pixel_bytes))
+        pix_ms = float(np.mean(pixel_ms)) if pixel_ms else float("nan")
+        achieved = pix_bytes / (pix_ms * 1e-3) / 1e9 if pix_ms == pix_ms and pix_ms > 0 else None
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "pixel_fuse_ncu.json")))
+            traffic = prof.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        frames = a.steps * B * world
+        value = frames / (elapsed_ms * 1e-3)
+        alg_path = float(np.mean(per_batch_alg)) / B
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 clouds / f64 reprojection, plane and k-NN arithmetic", "data": "synthetic",
+            "config": {"workload": workload_name(a), "height": H, "width": W, "frames_per_step": B,
+                       "batches_in_flight": a.slots, "cuda_graphs": not a.no_graph,
+                       "l2_policy": f"inputs larger than L2: {nb} distinct batches ({input_bytes / 1e6:.0f} MB) cycled",
+                       "parallelism": f"frame-parallel x{world} (no collective on the data path)",
+                       "params": "reference literals (semantic_depth.py:206-309), approach=both, SOR k=10, ROR r=0.5/80"},
+            "impl": "b200",
+            "gpu_launches": int(pipe.slots[0].engine.kernel_count(P)) * a.steps,
+            "result_mismatches_vs_first_pass": mism,
+            "answers_frame0": {"rw": float(expected[0].rw[0]), "f2f": float(expected[0].f2f[0]), "counts": counts0},
+            "clocks": sampler.summary(),
+            "host_wall_ms": wall * 1e3,
+            "batch_latency_ms": {"mean": float(np.mean(total_ms)) if total_ms else None,
+                                 "note": "first to last kernel of one batch, CUDA events, while other batches overlap"},
+            "roofline": {"kernel": "sd::pixel_fuse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": pix_bytes, "kernel_ms": pix_ms, "peak_source": peak_src,
+                         "note": "kernel time measured concurrently with other batches' kernels (pipelined run)"},
+            "roofline_path": {"bound": "hbm", "algorithmic_bytes_per_frame": alg_path,
+                              "achieved": alg_path * value / world / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                              "frac": alg_path * value / world / 1e9 / peak_gbs,
+                              "note": "SURVEY.md 8d B_alg x frames/s per GPU; k-NN / radius search are L2+fp64 bound, not HBM"},
+        }
+        if e2e:
+            ke, ems = e2e
+            line["e2e"] = {"value": ke * B * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * HW * 20,
+                           "d2h_bytes_per_step": B * 328, "steps": ke,
+                           "api": "FramePipeline.submit_host (pinned host inputs, copies pipelined over the slots)"}
+        if world == 1 and not a.skip_cpu_baseline:
+            try:
+                from oracle.cpu_baseline import CpuBaseline
+                cb = CpuBaseline(H, W, procs=a.cpu_procs or None)
+                wall_s, n, answers = cb.step()
+                cb.close()
+                line["cpu_baseline"] = {"value": n / wall_s, "unit": UNIT, "cores": cb.cores_used, "kind": "port",
+                                        "sample": cb.describe(), "host_cores": os.cpu_count(), "wall_s": wall_s}
+            except Exception as e:   # the baseline is a reported number, never a reason to lose the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

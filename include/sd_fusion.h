@@ -237,6 +237,9 @@ int sd_fuse_frames(const float* d_logits, const float* d_disp, int batch, int he
                    const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
                    SdFrameResult* d_results, SdWorkspace* ws, void* stream);
 
+/* Number of kernels one sd_fuse_frames call launches for these parameters (independent of batch). */
+int sd_fuse_kernel_count(const SdParams* params, int with_ransac);
+
 /* Same through HOST buffers (the reference-facing call: NumPy arrays in, results out): copies the
  * inputs host->device, runs sd_fuse_frames and copies the results back, all on `stream`, then
  * synchronises.  d_logits_stage / d_disp_stage are caller-owned device staging buffers. */
@@ -244,6 +247,18 @@ int sd_fuse_frames_host(const float* h_logits, const float* h_disp, int batch, i
                         const SdCamera* cam, const SdParams* params,
                         float* d_logits_stage, float* d_disp_stage, SdFrameResult* d_results,
                         SdFrameResult* h_results, SdWorkspace* ws, void* stream);
+
+/* Optional device-side timing of the fused call: when enabled, sd_fuse_frames records CUDA events on
+ * `stream` before / after the pixel-stage kernel and after the last kernel (skipped while the stream is
+ * being captured into a CUDA graph).  sd_ws_stage_elapsed_ms: which = 0 pixel-stage kernel,
+ * 1 = whole fused call; the stream must have been synchronised past the call. */
+int sd_ws_enable_timing(SdWorkspace* ws, int enable);
+/* Restrict the next sd_fuse_frames calls to a subset of the path: bit 0 = pixel stage, bit 1 = cloud
+ * stages + answers (default 3 = everything).  Lets a caller capture the two halves into separate CUDA
+ * graphs and time the pixel-stage kernel with its own events (events recorded inside a captured graph
+ * cannot be used with cudaEventElapsedTime). */
+int sd_ws_set_stage_mask(SdWorkspace* ws, int mask);
+int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms);
 
 /* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):
  * which = 0 road (after ROR), 1 left fence (after plane filter), 2 right fence. */

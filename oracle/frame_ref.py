@@ -87,7 +87,7 @@ def reproject_to_3d(disp, q32):
 # ----------------------------------------------------------------------------------------------
 # Open3D stand-ins (parity unpinned: Open3D is not vendored by the reference nor installable here)
 # ----------------------------------------------------------------------------------------------
-def knn_mean_distances(points, nb_neighbors):
+def knn_mean_distances(points, nb_neighbors, workers=1):
     """Mean of the distances to the k nearest neighbours (self included, distance 0), fp64.
 
     Open3D <= 0.7 ``RemoveStatisticalOutliers``: FLANN KNN on the fp64 cloud returns squared
@@ -102,7 +102,7 @@ def knn_mean_distances(points, nb_neighbors):
     k = min(int(nb_neighbors), n)
     if n == 0 or k == 0:
         return np.zeros(n, dtype=np.float64), k
-    _, idx = cKDTree(p).query(p, k=k)
+    _, idx = cKDTree(p).query(p, k=k, workers=workers)
     idx = idx.reshape(n, k)
     diff = p[idx] - p[:, None, :]
     d2 = (diff[..., 0] * diff[..., 0] + diff[..., 1] * diff[..., 1]) + diff[..., 2] * diff[..., 2]
@@ -126,27 +126,27 @@ def sor_threshold(avg, std_ratio):
     return cloud_mean + std_ratio * std_dev, cloud_mean, std_dev
 
 
-def keep_statistical_outlier_removal(points, nb_neighbors, std_ratio):
+def keep_statistical_outlier_removal(points, nb_neighbors, std_ratio, workers=1):
     """Kept indices (ascending) of Open3D statistical_outlier_removal; semantic_depth.py:234-236."""
     n = np.asarray(points).shape[0]
     if n == 0:
         return np.zeros(0, dtype=np.int64), np.zeros(0), (np.nan, np.nan, np.nan)
-    avg, _ = knn_mean_distances(points, nb_neighbors)
+    avg, _ = knn_mean_distances(points, nb_neighbors, workers)
     thr, mu, sd = sor_threshold(avg, std_ratio)
     return np.flatnonzero((avg > 0) & (avg < thr)), avg, (thr, mu, sd)
 
 
-def radius_counts(points, radius):
+def radius_counts(points, radius, workers=1):
     """Number of points within ``radius`` (self included; boundary d == r counted, cKDTree rule)."""
     p = np.ascontiguousarray(points, dtype=np.float64)
     if p.shape[0] == 0:
         return np.zeros(0, dtype=np.int64)
-    return np.asarray(cKDTree(p).query_ball_point(p, radius, return_length=True), dtype=np.int64)
+    return np.asarray(cKDTree(p).query_ball_point(p, radius, return_length=True, workers=workers), dtype=np.int64)
 
 
-def keep_radius_outlier_removal(points, nb_points, radius):
+def keep_radius_outlier_removal(points, nb_points, radius, workers=1):
     """Kept indices of Open3D radius_outlier_removal: count > nb_points; semantic_depth.py:238-241."""
-    return np.flatnonzero(radius_counts(points, radius) > nb_points)
+    return np.flatnonzero(radius_counts(points, radius, workers) > nb_points)
 
 
 def statistical_outlier_removal(points, colors, nb_neighbors, std_ratio):
@@ -237,7 +237,7 @@ class _Cloud:
         return self.pts.shape[0]
 
 
-def fuse_frame(logits, disp, q32, disparity_mult, params=None, hypotheses=None, keep_clouds=False):
+def fuse_frame(logits, disp, q32, disparity_mult, params=None, hypotheses=None, keep_clouds=False, workers=1):
     """Run the reference's fusion section on one frame and return every observable of it.
 
     ``params`` is any object with the attribute names of ``semantic_depth_b200.params.FusionParams``
@@ -300,11 +300,11 @@ def fuse_frame(logits, disp, q32, disparity_mult, params=None, hypotheses=None, 
     road = mad_stage(road, 0, g("road_mad_x_thr", 2.0), "road_mad_x")
     road, _ = plane_stage(road, 1, g("road_plane_thr", 5.0), "road_plane", "road", EMPTY_ROAD)
     if g("use_sor", True):
-        keep, avg, thr3 = keep_statistical_outlier_removal(road.pts, g("sor_nb_neighbors", 10), g("sor_std_ratio", 0.5))
+        keep, avg, thr3 = keep_statistical_outlier_removal(road.pts, g("sor_nb_neighbors", 10), g("sor_std_ratio", 0.5), workers)
         out["sor"] = {"avg": avg, "thr": thr3[0], "mean": thr3[1], "std": thr3[2]}
         road = stage(road, keep, "road_sor")
     if g("use_ror", True):
-        road = stage(road, keep_radius_outlier_removal(road.pts, g("ror_nb_points", 80), g("ror_radius", 0.5)), "road_ror")
+        road = stage(road, keep_radius_outlier_removal(road.pts, g("ror_nb_points", 80), g("ror_radius", 0.5), workers), "road_ror")
     road = _Cloud(road.pts.astype(np.float64), road.src)                            # :244 Open3D -> fp64
     if len(road) == 0:
         out["status"] |= EMPTY_ROAD

@@ -86,7 +86,11 @@ SIGNATURES = {
     "sd_ransac_score": (_I, [_P, _P, _P, _I, _I, C.c_double, _P, _I, _P, C.POINTER(C.c_int32),
                              C.POINTER(C.c_double), _P, _P]),
     "sd_fuse_frames": (_I, [_P, _P, _I, _I, _I, C.POINTER(SdCamera), C.POINTER(SdParams), _P, _P, _P, _I, _P, _P, _P]),
+    "sd_fuse_kernel_count": (_I, [C.POINTER(SdParams), _I]),
     "sd_fuse_frames_host": (_I, [_P, _P, _I, _I, _I, C.POINTER(SdCamera), C.POINTER(SdParams), _P, _P, _P, _P, _P, _P]),
+    "sd_ws_enable_timing": (_I, [_P, _I]),
+    "sd_ws_set_stage_mask": (_I, [_P, _I]),
+    "sd_ws_stage_elapsed_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
     "sd_ws_cloud": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sd_ws_stage_src": (_I, [_P, _I, _I, C.POINTER(_P)]),
 }

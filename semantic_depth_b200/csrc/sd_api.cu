@@ -94,6 +94,7 @@ struct WsPriv {
     const int32_t* hyp_road; const int32_t* hyp_left; const int32_t* hyp_right; int n_hyp;
     SdFrameResult* results;
     double cell_scale;
+    cudaEvent_t ev_t[3]; bool timing; int stage_mask;
 };
 
 size_t carve_all(SdWorkspace* ws, Carver& c) {
@@ -286,6 +287,8 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaStreamCreateWithFlags(&pv->side_stream, cudaStreamNonBlocking));
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_fork, cudaEventDisableTiming));
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) SD_CUDA_TRY(cudaEventCreate(&pv->ev_t[i]));
+    pv->timing = false; pv->stage_mask = 3;
     const char* e = getenv("SD_FUSE_SINGLE_STREAM");
     pv->single_stream = (e && e[0] == '1');
     const char* cs = getenv("SD_KNN_CELL_SCALE");
@@ -303,6 +306,7 @@ extern "C" void sd_ws_destroy(SdWorkspace* ws) {
         if (pv->side_stream) cudaStreamDestroy(pv->side_stream);
         if (pv->ev_fork) cudaEventDestroy(pv->ev_fork);
         if (pv->ev_join) cudaEventDestroy(pv->ev_join);
+        for (int i = 0; i < 3; ++i) if (pv->ev_t[i]) cudaEventDestroy(pv->ev_t[i]);
         cudaFreeHost(ws->h_pinned);
     }
     delete ws;
@@ -677,12 +681,19 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     const FusedTables& T = pv->t;
     const int B = batch, cap = ws->cap;
     const int cnt_stride = (int)(sizeof(FrameState) / sizeof(int32_t));
+    cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap_st);
+    const bool timing = pv->timing && cap_st == cudaStreamCaptureStatusNone;
+    const bool do_pixel = (pv->stage_mask & 1) != 0, do_cloud = (pv->stage_mask & 2) != 0;
     // ---- pixel stage: rA <- road (z cut applied), fA <- fence
-    rc = sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
+    if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[0], st));
+    rc = !do_pixel ? SD_OK : sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
                          ws->road[0], ws->fence[0], cap,
                          &ws->fs[0].n[SD_CNT_ROAD_GATHER], &ws->fs[0].n[SD_CNT_ROAD_Z], &ws->fs[0].n[SD_CNT_FENCE_GATHER], cnt_stride,
                          nullptr, nullptr, nullptr, ws->pstatus, ws->pctl, ws->pix_tiles, st);
     if (rc) return rc;
+    if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[1], st));
+    if (!do_cloud) return SD_OK;
     cudaStream_t sf = st;    // fence chain stream
     const bool fork = P.approach_both && !pv->single_stream;
     if (fork) {
@@ -727,7 +738,22 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     }
     SD_RUN(sd_launch_finalize(T.fin, B, &P, st));
 #undef SD_RUN
+    if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[2], st));
     return SD_OK;
+}
+
+extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
+    if (!P) return 0;
+    const int sel = 3, ransac = with_ransac ? 3 : 0;
+    int n = 1;                                   // pixel stage
+    n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
+    if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
+    if (P->use_sor) n += 1;
+    if (P->use_ror) n += 1;
+    n += 1 + 1;                                  // final road compaction, slab
+    if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain
+    n += 1;                                      // finalize
+    return n;
 }
 
 extern "C" int sd_fuse_frames_host(const float* h_logits, const float* h_disp, int batch, int height, int width,
@@ -744,6 +770,25 @@ extern "C" int sd_fuse_frames_host(const float* h_logits, const float* h_disp, i
     if (rc) return rc;
     SD_CUDA_TRY(cudaMemcpyAsync(h_results, d_results, sizeof(SdFrameResult) * batch, cudaMemcpyDeviceToHost, st));
     SD_CUDA_TRY(cudaStreamSynchronize(st));
+    return SD_OK;
+}
+
+extern "C" int sd_ws_enable_timing(SdWorkspace* ws, int enable) {
+    if (!ws) return fail(SD_ERR_INVALID, "sd_ws_enable_timing: null workspace");
+    priv(ws)->timing = enable != 0;
+    return SD_OK;
+}
+
+extern "C" int sd_ws_set_stage_mask(SdWorkspace* ws, int mask) {
+    if (!ws || mask < 1 || mask > 3) return fail(SD_ERR_INVALID, "sd_ws_set_stage_mask: mask must be 1, 2 or 3");
+    priv(ws)->stage_mask = mask;
+    return SD_OK;
+}
+
+extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
+    if (!ws || !h_ms || which < 0 || which > 1) return fail(SD_ERR_INVALID, "sd_ws_stage_elapsed_ms: bad argument");
+    WsPriv* pv = priv(ws);
+    SD_CUDA_TRY(cudaEventElapsedTime(h_ms, pv->ev_t[0], pv->ev_t[which == 0 ? 1 : 2]));
     return SD_OK;
 }
 

@@ -198,6 +198,23 @@ class FusionEngine:
         raw = np.frombuffer(self._results_host[:nbytes].numpy().tobytes(), dtype=RESULT_DTYPE).copy()
         return FusionResult(raw)
 
+    def kernel_count(self, params: FusionParams | None = None, with_ransac: bool = False) -> int:
+        ps = params_struct(params or FusionParams())
+        return int(self.lib.sd_fuse_kernel_count(C.byref(ps), int(with_ransac)))
+
+    def enable_timing(self, enable: bool = True):
+        """Record CUDA events around the pixel-stage kernel and the whole fused call (see sd_fusion.h)."""
+        check(self.lib.sd_ws_enable_timing(self._ws, int(enable)), "sd_ws_enable_timing")
+
+    def set_stage_mask(self, mask: int = 3):
+        """1 = pixel stage only, 2 = cloud stages + answers only, 3 = the whole path (default)."""
+        check(self.lib.sd_ws_set_stage_mask(self._ws, int(mask)), "sd_ws_set_stage_mask")
+
+    def stage_ms(self, which: str = "pixel") -> float:
+        ms = C.c_float(0)
+        check(self.lib.sd_ws_stage_elapsed_ms(self._ws, {"pixel": 0, "total": 1}[which], C.byref(ms)), "sd_ws_stage_elapsed_ms")
+        return float(ms.value)
+
     def final_cloud(self, frame: int, which: str = "road"):
         """(points [N,3] fp32, src [N] int32) of a frame's final road / left / right cloud (device)."""
         idx = {"road": 0, "left": 1, "right": 2}[which]

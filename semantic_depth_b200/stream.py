@@ -1,0 +1,206 @@
+"""Frame streams: pipelined batches on one GPU and frame-parallel sharding across GPUs.
+
+The reference processes a folder / video one frame at a time in a Python ``for`` loop
+(/root/reference/semantic_depth.py:867-901, semantic_depth_cityscapes_sequence.py:689-701).  Frames
+are independent, so here
+
+* ``FramePipeline`` keeps several batches in flight on one GPU (one workspace + stream + CUDA graph
+  per slot, round robin), hiding the ~45 dependent kernel boundaries of one batch behind the other
+  batches; host inputs are copied H2D on the slot's stream so copies overlap compute;
+* ``shard_frames`` / ``gather_results`` split a stream of frames over the ranks of a
+  ``torch.distributed`` job (one process per GPU).  There is no collective on the data path: the
+  only exchange is one end-of-run all_gather of the 24-byte answers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import SdFrameResult
+from .engine import FusionEngine, FusionResult, RESULT_DTYPE
+from .params import FusionParams, Intrinsics
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU sharding (host logic; covered by world_size-2 gloo tests on CPU)
+# ---------------------------------------------------------------------------------------------
+def shard_frames(n_frames: int, rank: int, world: int) -> range:
+    """Contiguous, balanced chunk of frame indices for ``rank`` (first ``n % world`` ranks get one more)."""
+    if world < 1 or not (0 <= rank < world) or n_frames < 0:
+        raise ValueError("bad shard request")
+    base, extra = divmod(n_frames, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def pack_answers(rw, f2f, status) -> torch.Tensor:
+    """[n,3] float64: rw, f2f, status (status is exact in fp64)."""
+    out = np.stack([np.asarray(rw, np.float64), np.asarray(f2f, np.float64), np.asarray(status, np.float64)], axis=1)
+    return torch.from_numpy(np.ascontiguousarray(out))
+
+
+def gather_results(local: torch.Tensor, n_frames: int, device=None):
+    """All-gather the per-rank [n_local,3] answers into the global [n_frames,3] array (frame order).
+
+    Uses the default process group (nccl on GPUs, gloo in the CPU tests).  Ranks hold the chunks of
+    ``shard_frames``; chunks are padded to the largest chunk for the collective."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return local.clone()
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [len(shard_frames(n_frames, r, world)) for r in range(world)]
+    if local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {local.shape[0]} frames, expected {sizes[rank]}")
+    pad = max(sizes) if sizes else 0
+    buf = torch.full((pad, 3), float("nan"), dtype=torch.float64, device=device or local.device)
+    buf[: local.shape[0]] = local.to(buf.device)
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf)
+    return torch.cat([o[:s] for o, s in zip(out, sizes)], dim=0).cpu()
+
+
+# ---------------------------------------------------------------------------------------------
+# pipelined batches on one GPU
+# ---------------------------------------------------------------------------------------------
+class _Slot:
+    def __init__(self, height, width, batch, device, max_hyp=0):
+        self.engine = FusionEngine(height, width, max_frames=batch, max_hypotheses=max_hyp, device=device)
+        self.stream = torch.cuda.Stream(device=device)
+        self.done = torch.cuda.Event()
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.graphs = {}           # key -> CUDAGraph
+        self.stage_logits = None   # device staging for host inputs
+        self.stage_disp = None
+        self.host_results = torch.zeros(batch * C.sizeof(SdFrameResult), dtype=torch.uint8).pin_memory()
+        self.busy = False
+        self.tag = None
+        self.nbytes = 0
+
+
+class FramePipeline:
+    """Round-robin pipeline of ``slots`` batches in flight on one GPU.
+
+    ``submit_*`` enqueues a batch on the next slot (waiting for that slot's previous batch first and
+    returning its result, if any); ``drain`` returns the results still in flight.  Results come back
+    in submission order as ``(tag, FusionResult)``.
+    """
+
+    def __init__(self, height: int, width: int, batch: int, slots: int = 2, device="cuda:0",
+                 params: FusionParams | None = None, use_graphs: bool = True, timing: bool = False):
+        self.height, self.width, self.batch = height, width, batch
+        self.device = torch.device(device)
+        self.params = params or FusionParams()
+        self.use_graphs = use_graphs
+        self.slots = [_Slot(height, width, batch, self.device) for _ in range(slots)]
+        self.timing = timing
+        self.pixel_ms: list[float] = []
+        self.total_ms: list[float] = []
+        self._next = 0
+
+    # -- internals ---------------------------------------------------------------------------------
+    def _retire(self, slot: _Slot):
+        if not slot.busy:
+            return None
+        slot.done.synchronize()
+        if self.timing:
+            self.pixel_ms.append(slot.ev[0].elapsed_time(slot.ev[1]))
+            self.total_ms.append(slot.ev[0].elapsed_time(slot.ev[2]))
+        raw = np.frombuffer(slot.host_results[: slot.nbytes].numpy().tobytes(), dtype=RESULT_DTYPE).copy()
+        slot.busy = False
+        return slot.tag, FusionResult(raw)
+
+    def _capture(self, slot: _Slot, logits, disp, intr, mask):
+        eng = slot.engine
+        eng.set_stage_mask(mask)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=slot.stream):
+            eng.enqueue(logits, disp, intr, self.params)
+        eng.set_stage_mask(3)
+        return g
+
+    def _launch(self, slot: _Slot, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, key):
+        """Enqueue one batch on the slot's stream.  With timing on, the pixel stage and the cloud stages
+        are two graphs (or two eager calls) so that torch events can bracket the pixel-stage kernel."""
+        eng = slot.engine
+        b = logits.shape[0]
+        if self.use_graphs:
+            g = slot.graphs.get(key)
+            if g is None:
+                eng.enqueue(logits, disp, intr, self.params)          # eager once: builds the job tables
+                slot.stream.synchronize()
+                g = ((self._capture(slot, logits, disp, intr, 1), self._capture(slot, logits, disp, intr, 2))
+                     if self.timing else (self._capture(slot, logits, disp, intr, 3),))
+                slot.graphs[key] = g
+            if self.timing:
+                slot.ev[0].record(slot.stream); g[0].replay(); slot.ev[1].record(slot.stream); g[1].replay()
+                slot.ev[2].record(slot.stream)
+            else:
+                g[0].replay()
+        elif self.timing:
+            slot.ev[0].record(slot.stream)
+            eng.set_stage_mask(1); eng.enqueue(logits, disp, intr, self.params)
+            slot.ev[1].record(slot.stream)
+            eng.set_stage_mask(2); eng.enqueue(logits, disp, intr, self.params)
+            eng.set_stage_mask(3)
+            slot.ev[2].record(slot.stream)
+        else:
+            eng.enqueue(logits, disp, intr, self.params)
+        slot.nbytes = b * C.sizeof(SdFrameResult)
+        slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
+        slot.done.record(slot.stream)
+        slot.busy = True
+
+    def _take_slot(self):
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        return slot, self._retire(slot)
+
+    # -- public ------------------------------------------------------------------------------------
+    def submit_device(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, tag=None):
+        """Inputs already resident on the GPU (fixed tensors are replayed through a cached CUDA graph)."""
+        slot, finished = self._take_slot()
+        with torch.cuda.stream(slot.stream):
+            slot.tag = tag
+            self._launch(slot, logits, disp, intr, key=(logits.data_ptr(), disp.data_ptr(), logits.shape[0]))
+        return finished
+
+    def warm_device(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, tag=None):
+        """Run one batch through EVERY slot (captures each slot's graph for these tensors); returns the results."""
+        out = []
+        for _ in range(len(self.slots)):
+            fin = self.submit_device(logits, disp, intr, tag)
+            if fin:
+                out.append(fin)
+        return out + self.drain()
+
+    def submit_host(self, logits, disp, intr: Intrinsics, tag=None):
+        """Host inputs (NumPy arrays or CPU tensors; pinned memory makes the copy asynchronous)."""
+        slot, finished = self._take_slot()
+        lg = logits if isinstance(logits, torch.Tensor) else torch.from_numpy(logits)
+        dp = disp if isinstance(disp, torch.Tensor) else torch.from_numpy(disp)
+        b = lg.shape[0]
+        with torch.cuda.stream(slot.stream):
+            if slot.stage_logits is None:
+                slot.stage_logits = torch.empty((self.batch, self.height * self.width, 3), dtype=torch.float32, device=self.device)
+                slot.stage_disp = torch.empty((self.batch, 2, self.height, self.width), dtype=torch.float32, device=self.device)
+            slot.stage_logits[:b].copy_(lg, non_blocking=True)
+            slot.stage_disp[:b].copy_(dp, non_blocking=True)
+            slot.tag = tag
+            self._launch(slot, slot.stage_logits[:b], slot.stage_disp[:b], intr, key=("host", b))
+        return finished
+
+    def drain(self):
+        out = []
+        for _ in range(len(self.slots)):
+            slot = self.slots[self._next]
+            self._next = (self._next + 1) % len(self.slots)
+            r = self._retire(slot)
+            if r is not None:
+                out.append(r)
+        return out
+
+    def close(self):
+        for s in self.slots:
+            s.engine.close()

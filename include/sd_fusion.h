@@ -260,6 +260,11 @@ int sd_ws_enable_timing(SdWorkspace* ws, int enable);
 int sd_ws_set_stage_mask(SdWorkspace* ws, int mask);
 int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms);
 
+/* Developer counters of the organized neighbour search of `frame` (cumulative since sd_ws_create):
+ * k-NN queries, queued hard k-NN queries, window-certificate failures, ray-bound failures, list overflows,
+ * -, queued hard radius queries, sum of per-query candidate-list lengths.  Synchronises the device. */
+int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8);
+
 /* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):
  * which = 0 road (after ROR), 1 left fence (after plane filter), 2 right fence. */
 int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,

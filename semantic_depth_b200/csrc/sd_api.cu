@@ -83,7 +83,7 @@ struct FusedTables {
     CompactJob* c_road_y; CompactJob* c_road_x; CompactJob* c_road_plane; CompactJob* c_road_final;
     CompactJob* c_fence_y; CompactJob* c_fence_z; CompactJob* c_split; CompactJob* c_side_x; CompactJob* c_side_plane;
     PlaneJob* p_road; PlaneJob* p_side;
-    MeanJob* m_fence; SlabJob* s_road; KnnJob* k_road; FinalJob* fin;
+    MeanJob* m_fence; SlabJob* s_road; KnnJob* k_road; FinalJob* fin; OrgJob* o_road;
     RansacJob* r_road; RansacJob* r_side;
 };
 
@@ -93,7 +93,9 @@ struct WsPriv {
     bool single_stream;
     const int32_t* hyp_road; const int32_t* hyp_left; const int32_t* hyp_right; int n_hyp;
     SdFrameResult* results;
+    SdCamera cam;
     double cell_scale;
+    bool organized;
     cudaEvent_t ev_t[3]; bool timing; int stage_mask;
 };
 
@@ -112,8 +114,9 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->cctl = c.take<ScanCtl>((size_t)F * kChains);
     ws->partials = c.take<double>((size_t)F * kChains * kPlaneBlocks * kPlaneSums);
     ws->ptick = c.take<uint32_t>((size_t)F * kChains);
-    ws->pstatus = c.take<unsigned long long>((size_t)F * ws->pix_tiles);
-    ws->pctl = c.take<ScanCtl>(F);
+    ws->pflags = c.take<uint8_t>((size_t)F * ws->height * ws->width);
+    ws->ptcounts = c.take<int32_t>((size_t)F * ws->pix_tiles * 4);
+    ws->ptoffs = c.take<int32_t>((size_t)F * ws->pix_tiles * 2);
     ws->lmask = c.take<double>(ws->width); ws->rmask = c.take<double>(ws->width);
     ws->gs = c.take<GridState>(F);
     ws->cell_count = c.take<int32_t>(F * ((size_t)ws->cell_cap + 8));
@@ -124,6 +127,10 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->avg = c.take<double>(F * cap); ws->savg = c.take<double>(F * cap);
     ws->cnt = c.take<int32_t>(F * cap);
     ws->knn_part = c.take<double>((size_t)F * kKnnMaxBlocks * 3);
+    ws->dense = c.take<float4>((size_t)F * ws->height * ws->width);
+    ws->ost = c.take<OrgState>(F);
+    ws->queue_knn = c.take<int32_t>(F * cap);
+    ws->queue_ror = c.take<int32_t>(F * cap);
     ws->gstatus = c.take<unsigned long long>((size_t)F * ws->grid_tiles);
     ws->gctl = c.take<ScanCtl>(F);
     const size_t mh = (size_t)(ws->max_hyp > 0 ? ws->max_hyp : 1);
@@ -249,12 +256,12 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaMemsetAsync(ws->cstatus, 0, sizeof(unsigned long long) * max_frames * kChains * ws->max_tiles, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->cctl, 0, sizeof(ScanCtl) * max_frames * kChains, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->ptick, 0, sizeof(uint32_t) * max_frames * kChains, st));
-    SD_CUDA_TRY(cudaMemsetAsync(ws->pstatus, 0, sizeof(unsigned long long) * max_frames * ws->pix_tiles, st));
-    SD_CUDA_TRY(cudaMemsetAsync(ws->pctl, 0, sizeof(ScanCtl) * max_frames, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->cell_count, 0, sizeof(int32_t) * max_frames * ((size_t)ws->cell_cap + 8), st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->gstatus, 0, sizeof(unsigned long long) * max_frames * ws->grid_tiles, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->gctl, 0, sizeof(ScanCtl) * max_frames, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->scratch, 0, ws->scratch_bytes, st));
+    SD_CUDA_TRY(cudaMemsetAsync(ws->ost, 0, sizeof(OrgState) * max_frames, st));
+    { int rc_fill = sd_launch_org_fill(ws->dense, (size_t)max_frames * height * width, st); if (rc_fill) return rc_fill; }
     // GridState: bbox keys start at (+max, 0); FrameState slab keys likewise
     {
         std::vector<GridState> g(max_frames);
@@ -291,6 +298,8 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     pv->timing = false; pv->stage_mask = 3;
     const char* e = getenv("SD_FUSE_SINGLE_STREAM");
     pv->single_stream = (e && e[0] == '1');
+    const char* sm = getenv("SD_SOR_MODE");
+    pv->organized = (sm && strcmp(sm, "organized") == 0);     // default: world-space grid search
     const char* cs = getenv("SD_KNN_CELL_SCALE");
     pv->cell_scale = cs ? atof(cs) : 1.0;
     if (!(pv->cell_scale > 0.0)) pv->cell_scale = 1.0;
@@ -358,7 +367,7 @@ extern "C" int sd_pixel_fuse(const float* d_logits, const float* d_disp, const d
     return sd_launch_pixel(d_logits, d_disp, d_lmask ? d_lmask : ws->lmask, d_rmask ? d_rmask : ws->rmask,
                            batch, height, width, *cam, prob_thr, road_z_to_meter, flags, road, fence, height * width,
                            d_counts + 0, d_counts + 1, d_counts + 2, 3, d_labels, d_points, d_disp_pp,
-                           ws->pstatus, ws->pctl, ws->pix_tiles, (cudaStream_t)stream);
+                           ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, (cudaStream_t)stream);
 }
 
 extern "C" int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream) {
@@ -535,9 +544,10 @@ namespace {
 
 bool same_params(const SdParams& a, const SdParams& b) { return memcmp(&a, &b, sizeof(SdParams)) == 0; }
 
-int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const int32_t* hyp_road, const int32_t* hyp_left,
+int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera& cam, const int32_t* hyp_road, const int32_t* hyp_left,
                        const int32_t* hyp_right, int n_hyp, SdFrameResult* d_results, cudaStream_t st) {
     WsPriv* pv = priv(ws);
+    pv->cam = cam;
     JobBuilder jb(ws);
     FusedTables& T = pv->t;
     memset(&T, 0, sizeof(T));
@@ -553,7 +563,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const int32_t*
     SD_ALLOC(c_split, CompactJob, 2 * B); SD_ALLOC(c_side_x, CompactJob, 2 * B); SD_ALLOC(c_side_plane, CompactJob, 2 * B);
     SD_ALLOC(p_road, PlaneJob, B); SD_ALLOC(p_side, PlaneJob, 2 * B);
     SD_ALLOC(m_fence, MeanJob, B); SD_ALLOC(s_road, SlabJob, B); SD_ALLOC(k_road, KnnJob, B); SD_ALLOC(fin, FinalJob, B);
-    SD_ALLOC(r_road, RansacJob, B); SD_ALLOC(r_side, RansacJob, 2 * B);
+    SD_ALLOC(r_road, RansacJob, B); SD_ALLOC(r_side, RansacJob, 2 * B); SD_ALLOC(o_road, OrgJob, B);
 #undef SD_ALLOC
     const size_t mh = (size_t)(ws->max_hyp > 0 ? ws->max_hyp : 1);
     for (int f = 0; f < B; ++f) {
@@ -595,6 +605,23 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const int32_t*
           if (P.use_sor) { p.aux = h_k_road[f].avg; p.p_d = fs->sor_stats + 2; }
           if (P.use_ror) { p.aux2 = h_k_road[f].cnt; }
           fill_compact(h_c_road_final[f], rB, &fs->n[SD_CNT_ROAD_PLANE], rA, &fs->n[SD_CNT_ROAD_ROR], p, ws, f, 0); }
+        // organized (per-pixel) search: the plane filter also writes the survivors into the frame's pixel image,
+        // the final compaction restores its all-inf invariant
+        { OrgJob& o = h_o_road[f]; memset(&o, 0, sizeof(o));
+          o.x = rB.x; o.y = rB.y; o.z = rB.z; o.src = rB.src; o.n = &fs->n[SD_CNT_ROAD_PLANE];
+          o.dense = ws->dense + (size_t)f * ws->height * ws->width; o.st = ws->ost + f;
+          o.avg = h_k_road[f].avg; o.cnt = h_k_road[f].cnt;
+          o.queue_knn = ws->queue_knn + (size_t)f * cap; o.queue_ror = ws->queue_ror + (size_t)f * cap;
+          o.queue_bound = reinterpret_cast<float*>(h_k_road[f].savg);     // the grid path's scratch is free in this mode
+          o.stats = fs->sor_stats; o.n_alive = &fs->n_sor_alive;
+          o.height = ws->height; o.width = ws->width;
+          o.q03 = pv->cam.q03; o.q13 = pv->cam.q13; o.q23 = pv->cam.q23;
+          o.k = P.sor_nb_neighbors; o.std_ratio = P.sor_std_ratio; o.radius = P.ror_radius;
+          o.nb_points = P.ror_nb_points; o.use_sor = P.use_sor;
+          if (pv->organized && P.sor_nb_neighbors <= 32 && (P.use_sor || P.use_ror)) {
+              h_c_road_plane[f].dense = o.dense; h_c_road_plane[f].dense_mode = 1;
+              h_c_road_final[f].dense = o.dense; h_c_road_final[f].dense_mode = 2;
+          } }
         // slab min/max on rA                                               :254-259
         { SlabJob& s = h_s_road[f]; memset(&s, 0, sizeof(s));
           s.x = rA.x; s.z = rA.z; s.n = &fs->n[SD_CNT_ROAD_ROR]; s.lo = P.slab_lo; s.hi = P.slab_hi;
@@ -670,12 +697,13 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     const SdParams& P = *params;
     int rc;
     if (!ws->fused_ready || ws->fused_batch != batch || !same_params(ws->fused_params, P) || pv->hyp_road != d_hyp_road ||
-        pv->hyp_left != d_hyp_left || pv->hyp_right != d_hyp_right || pv->n_hyp != n_hyp || pv->results != d_results) {
+        pv->hyp_left != d_hyp_left || pv->hyp_right != d_hyp_right || pv->n_hyp != n_hyp || pv->results != d_results ||
+        memcmp(&pv->cam, cam, sizeof(SdCamera)) != 0) {
         cudaStreamCaptureStatus cst = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cst);
         if (cst != cudaStreamCaptureStatusNone)
             return fail(SD_ERR_UNSUPPORTED, "sd_fuse_frames: first call with new parameters must happen outside stream capture");
-        rc = build_fused_tables(ws, batch, P, d_hyp_road, d_hyp_left, d_hyp_right, n_hyp, d_results, st);
+        rc = build_fused_tables(ws, batch, P, *cam, d_hyp_road, d_hyp_left, d_hyp_right, n_hyp, d_results, st);
         if (rc) return rc;
     }
     const FusedTables& T = pv->t;
@@ -690,7 +718,7 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     rc = !do_pixel ? SD_OK : sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
                          ws->road[0], ws->fence[0], cap,
                          &ws->fs[0].n[SD_CNT_ROAD_GATHER], &ws->fs[0].n[SD_CNT_ROAD_Z], &ws->fs[0].n[SD_CNT_FENCE_GATHER], cnt_stride,
-                         nullptr, nullptr, nullptr, ws->pstatus, ws->pctl, ws->pix_tiles, st);
+                         nullptr, nullptr, nullptr, ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, st);
     if (rc) return rc;
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[1], st));
     if (!do_cloud) return SD_OK;
@@ -712,9 +740,15 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     if (d_hyp_road) SD_RUN(sd_launch_ransac(T.r_road, B, cap, n_hyp, st));
     SD_RUN(sd_launch_plane(T.p_road, B, cap, st));
     SD_RUN(sd_launch_compact(T.c_road_plane, B, cap, st));
-    if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
-    if (P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
-    if (P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
+    if (pv->organized && P.sor_nb_neighbors <= 32) {
+        if (P.use_sor) SD_RUN(sd_launch_org_knn(T.o_road, B, cap, P.sor_nb_neighbors, st));
+        if (P.use_sor && P.use_ror) SD_RUN(sd_launch_org_apply_sor(T.o_road, B, cap, st));
+        if (P.use_ror) SD_RUN(sd_launch_org_ror(T.o_road, B, cap, st));
+    } else {
+        if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
+        if (P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
+        if (P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
+    }
     SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
     SD_RUN(sd_launch_slab(T.s_road, B, cap, st));
     // ---- fence chain (stream sf)
@@ -745,11 +779,19 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
 extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     if (!P) return 0;
     const int sel = 3, ransac = with_ransac ? 3 : 0;
-    int n = 1;                                   // pixel stage
+    int n = 3;                                   // pixel stage: label, scan, scatter
     n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
-    if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
-    if (P->use_sor) n += 1;
-    if (P->use_ror) n += 1;
+    const char* sm = getenv("SD_SOR_MODE");
+    const bool organized = (sm && strcmp(sm, "organized") == 0) && P->sor_nb_neighbors <= 32;
+    if (organized) {
+        if (P->use_sor) n += 2;                  // k-NN main + hard
+        if (P->use_sor && P->use_ror) n += 1;    // apply the statistical filter to the pixel image
+        if (P->use_ror) n += 2;                  // radius main + hard
+    } else {
+        if (P->use_sor || P->use_ror) n += 4;    // grid: bbox, count, scan, scatter
+        if (P->use_sor) n += 1;
+        if (P->use_ror) n += 1;
+    }
     n += 1 + 1;                                  // final road compaction, slab
     if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain
     n += 1;                                      // finalize
@@ -789,6 +831,13 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
     if (!ws || !h_ms || which < 0 || which > 1) return fail(SD_ERR_INVALID, "sd_ws_stage_elapsed_ms: bad argument");
     WsPriv* pv = priv(ws);
     SD_CUDA_TRY(cudaEventElapsedTime(h_ms, pv->ev_t[0], pv->ev_t[which == 0 ? 1 : 2]));
+    return SD_OK;
+}
+
+extern "C" int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8) {
+    if (!ws || !h_out8 || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_debug_counters: bad argument");
+    SD_CUDA_TRY(cudaDeviceSynchronize());
+    SD_CUDA_TRY(cudaMemcpy(h_out8, ws->ost[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
     return SD_OK;
 }
 

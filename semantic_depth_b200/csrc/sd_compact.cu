@@ -147,9 +147,17 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
                 if (J.ox) J.ox[pos] = x[k];
                 if (J.oy) J.oy[pos] = y[k];
                 if (J.oz) J.oz[pos] = z[k];
-                if (J.osrc) J.osrc[pos] = J.src ? __ldg(J.src + base + k) : (base + k);
+                const int sidx = J.src ? __ldg(J.src + base + k) : (base + k);
+                if (J.osrc) J.osrc[pos] = sidx;
+                if (J.dense_mode == 1) J.dense[sidx] = make_float4(x[k], y[k], z[k], __int_as_float(pos));
                 ++pos;
             }
+        }
+        if (J.dense_mode == 2) {          // restore the organized buffer's all-inf invariant
+            const float inf = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int k = 0; k < kCompactItems; ++k)
+                if (base + k < n) J.dense[__ldg(J.src + base + k)] = make_float4(inf, inf, inf, inf);
         }
         __syncthreads();   // s_tile / s_excl are rewritten by the next iteration
     }

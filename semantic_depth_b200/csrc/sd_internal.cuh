@@ -74,6 +74,9 @@ struct CompactJob {
     uint32_t* frame_status;     // optional: OR `empty_bit` when the output is empty
     uint32_t empty_bit;
     int32_t max_tiles;
+    float4* dense;              // optional organized (per-pixel) copy of the cloud, indexed by src
+    int32_t dense_mode;         // 1: dense[src] = (x,y,z,bits(out index)) for kept points; 2: dense[src] = +inf for every input point
+    int32_t pad_;
 };
 
 // ---- plane fit -----------------------------------------------------------------------------------------
@@ -143,6 +146,33 @@ struct KnnJob {
 };
 constexpr int kKnnMaxBlocks = 148 * 16;
 
+// ---- organized (per-pixel) neighbour search of the fused path ---------------------------------------------------
+struct OrgState {
+    unsigned long long acc[3][2];   // exact fixed-point sums of avg, avg^2 and the count of avg > 0
+    uint32_t ticket;
+    int32_t qn_knn;                 // hard k-NN queries queued
+    int32_t qn_ror;                 // hard radius queries queued
+    int32_t pad_;
+    unsigned long long dbg[8];      // cumulative: 0 knn queries, 1 knn hard, 2 fail window cert, 3 fail ray bound,
+                                    //             4 list overflow, 5 ror queries, 6 ror hard, 7 sum of list counts
+};
+struct OrgJob {
+    const float* x; const float* y; const float* z; const int32_t* src; const int32_t* n;   // compact cloud (plane-filtered)
+    float4* dense;                  // [H*W] (x,y,z,bits(index)); +inf where no point
+    OrgState* st;
+    double* avg;                    // [cap] mean k-NN distance by compact index
+    int32_t* cnt;                   // [cap] radius counts by compact index (saturated at nb_points+1)
+    int32_t* queue_knn; int32_t* queue_ror;   // [cap] compact indices of the hard queries
+    float* queue_bound;             // [cap] per queued k-NN query: an upper bound of its k-th squared distance (inf: none)
+    double* stats;                  // mean, std, thr
+    int32_t* n_alive;
+    int32_t height, width;
+    float q03, q13, q23;            // ray of pixel (u,v): (u + q03, q13 - v, q23)
+    int32_t k;
+    double std_ratio, radius;
+    int32_t nb_points, use_sor;
+};
+
 // ---- RANSAC ----------------------------------------------------------------------------------------------
 struct RansacJob {
     const float* x; const float* y; const float* z; const int32_t* n;
@@ -160,6 +190,48 @@ struct FinalJob {
     FrameState* fs;
     SdFrameResult* out;
 };
+
+// ---- exact, order-independent accumulation of the cloud statistics ------------------------------------
+// The per-point means are bit-exact, but their summation order would depend on the (atomic) order of
+// points inside a cell.  Summing 2^-70 fixed-point images of the values in 128-bit integers is exact
+// and associative, so the cloud mean / std are deterministic run to run (and closer to the real sum
+// than any fp64 summation order).
+struct U128 { unsigned long long lo, hi; };
+__device__ __forceinline__ U128 to_fixed70(double v) {      // floor(v * 2^70) for finite v > 0, else 0
+    U128 r{0ull, 0ull};
+    if (!(v > 0.0)) return r;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const int e = (int)((bits >> 52) & 0x7ffull);
+    if (e == 0 || e == 0x7ff) return r;
+    const unsigned long long m = (bits & 0xfffffffffffffull) | (1ull << 52);
+    int sh = e - 1075 + 70;                                  // v = m * 2^(e-1075)
+    if (sh > 74) sh = 74;                                    // saturate (|v| >= 2^57 never happens for metres)
+    if (sh >= 64) { r.hi = m << (sh - 64); }
+    else if (sh > 0) { r.lo = m << sh; r.hi = m >> (64 - sh); }
+    else if (sh == 0) { r.lo = m; }
+    else if (sh > -64) { r.lo = m >> (-sh); }
+    return r;
+}
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+    U128 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull); return r;
+}
+__device__ __forceinline__ U128 warp_sum128(U128 v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        U128 t; t.lo = __shfl_xor_sync(SD_FULL, v.lo, o); t.hi = __shfl_xor_sync(SD_FULL, v.hi, o);
+        v = add128(v, t);
+    }
+    return v;
+}
+__device__ __forceinline__ void atomic_add128(unsigned long long* acc, U128 v) {
+    const unsigned long long old = atomicAdd(&acc[0], v.lo);
+    const unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
+    if (v.hi | carry) atomicAdd(&acc[1], v.hi + carry);
+}
+__device__ __forceinline__ double fixed70_to_double(unsigned long long lo, unsigned long long hi) {
+    return ((double)hi * 18446744073709551616.0 + (double)lo) * 8.470329472543003e-22;   // 2^-70
+}
+
 
 }  // namespace sd
 
@@ -179,8 +251,9 @@ struct SdWorkspace {
     double* partials;                    // [F][4][kPlaneBlocks*kPlaneSums]
     uint32_t* ptick;                     // [F][4]
     // pixel pass
-    unsigned long long* pstatus;         // [F][pix_tiles]
-    sd::ScanCtl* pctl;                   // [F]
+    uint8_t* pflags;                     // [F][H*W] per-pixel label / keep flags
+    int32_t* ptcounts;                   // [F][pix_tiles][4]
+    int32_t* ptoffs;                     // [F][pix_tiles][2]
     int pix_tiles;
     double* lmask; double* rmask;        // [width] blend ramps (uploaded at create)
     // grid / knn per frame
@@ -188,6 +261,7 @@ struct SdWorkspace {
     int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
     float* sx; float* sy; float* sz; int32_t* sorig;
     double* avg; double* savg; int32_t* cnt; double* knn_part;
+    float4* dense; sd::OrgState* ost; int32_t* queue_knn; int32_t* queue_ror;   // organized search (fused path)
     unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
     // ransac per (frame, chain 0..2)
     double* hyp_coeff; int32_t* hyp_counts; double* best_coeff;
@@ -211,6 +285,10 @@ int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStrea
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
 int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, cudaStream_t st);
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_org_fill(float4* dense, size_t count, cudaStream_t st);
+int sd_launch_org_knn(const sd::OrgJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
+int sd_launch_org_apply_sor(const sd::OrgJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_org_ror(const sd::OrgJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
 int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
@@ -218,4 +296,4 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
                     SdCloudBuf road, SdCloudBuf fence, int cap_stride,
                     int32_t* d_cnt_road_gather, int32_t* d_cnt_road_z, int32_t* d_cnt_fence, int cnt_stride,
                     uint8_t* d_labels, float* d_points, float* d_disp_pp,
-                    unsigned long long* status, sd::ScanCtl* ctl, int pix_tiles, cudaStream_t st);
+                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st);

@@ -168,47 +168,6 @@ __device__ __forceinline__ GridRt load_grid(const GridState* gs) {
     return g;
 }
 
-// ---- exact, order-independent accumulation of the cloud statistics ------------------------------------
-// The per-point means are bit-exact, but their summation order would depend on the (atomic) order of
-// points inside a cell.  Summing 2^-70 fixed-point images of the values in 128-bit integers is exact
-// and associative, so the cloud mean / std are deterministic run to run (and closer to the real sum
-// than any fp64 summation order).
-struct U128 { unsigned long long lo, hi; };
-__device__ __forceinline__ U128 to_fixed70(double v) {      // floor(v * 2^70) for finite v > 0, else 0
-    U128 r{0ull, 0ull};
-    if (!(v > 0.0)) return r;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
-    const int e = (int)((bits >> 52) & 0x7ffull);
-    if (e == 0 || e == 0x7ff) return r;
-    const unsigned long long m = (bits & 0xfffffffffffffull) | (1ull << 52);
-    int sh = e - 1075 + 70;                                  // v = m * 2^(e-1075)
-    if (sh > 74) sh = 74;                                    // saturate (|v| >= 2^57 never happens for metres)
-    if (sh >= 64) { r.hi = m << (sh - 64); }
-    else if (sh > 0) { r.lo = m << sh; r.hi = m >> (64 - sh); }
-    else if (sh == 0) { r.lo = m; }
-    else if (sh > -64) { r.lo = m >> (-sh); }
-    return r;
-}
-__device__ __forceinline__ U128 add128(U128 a, U128 b) {
-    U128 r; r.lo = a.lo + b.lo; r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull); return r;
-}
-__device__ __forceinline__ U128 warp_sum128(U128 v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        U128 t; t.lo = __shfl_xor_sync(SD_FULL, v.lo, o); t.hi = __shfl_xor_sync(SD_FULL, v.hi, o);
-        v = add128(v, t);
-    }
-    return v;
-}
-__device__ __forceinline__ void atomic_add128(unsigned long long* acc, U128 v) {
-    const unsigned long long old = atomicAdd(&acc[0], v.lo);
-    const unsigned long long carry = (old + v.lo < old) ? 1ull : 0ull;
-    if (v.hi | carry) atomicAdd(&acc[1], v.hi + carry);
-}
-__device__ __forceinline__ double fixed70_to_double(unsigned long long lo, unsigned long long hi) {
-    return ((double)hi * 18446744073709551616.0 + (double)lo) * 8.470329472543003e-22;   // 2^-70
-}
-
 template <int KCAP>
 struct Best {
     double d[KCAP];      // descending: d[0] is the current k-th smallest (the worst kept)
@@ -235,53 +194,124 @@ struct Best {
     }
 };
 
+// ---- slow exact path: fp64 keys, ring by ring (used when the fp32-keyed search cannot certify its set)
 template <int KCAP>
-__device__ __forceinline__ void scan_range(const KnnJob& J, int s, int e, float qx, float qy, float qz,
-                                           Best<KCAP>& best, float& worst32) {
+__device__ __forceinline__ void scan_range_exact(const KnnJob& J, int s, int e, float qx, float qy, float qz, Best<KCAP>& best) {
     for (int j = s; j < e; ++j) {
         const float px = __ldg(J.sx + j), py = __ldg(J.sy + j), pz = __ldg(J.sz + j);
-        const float fx = px - qx, fy = py - qy, fz = pz - qz;
-        const float d2f = (fx * fx + fy * fy) + fz * fz;       // relative error < 1e-6 (all terms >= 0)
-        if (d2f > worst32) continue;
         const double dx = (double)px - (double)qx, dy = (double)py - (double)qy, dz = (double)pz - (double)qz;
         const double d2 = (dx * dx + dy * dy) + dz * dz;
-        if (d2 < best.d[0]) {
-            best.insert(d2);
-            worst32 = __double2float_ru(best.d[0]) * 1.000002f;
-        }
+        if (d2 < best.d[0]) best.insert(d2);
     }
 }
 
 template <int KCAP>
+__device__ __noinline__ double knn_exact_sum(const KnnJob& J, const GridRt& g, float qx, float qy, float qz, double q0, double q1,
+                                              int c0, int c1, int keff) {
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    Best<KCAP> best; best.init(keff);
+    for (int r = 0;; ++r) {
+        const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
+        const int cl0 = max(lo0, 0), ch0 = min(hi0, g.d0 - 1);
+        for (int row = max(lo1, 0); row <= min(hi1, g.d1 - 1); ++row) {
+            const int rb = row * g.d0;
+            if (row == lo1 || row == hi1) {
+                scan_range_exact<KCAP>(J, J.cell_start[rb + cl0], J.cell_start[rb + ch0 + 1], qx, qy, qz, best);
+            } else {
+                if (lo0 >= 0) scan_range_exact<KCAP>(J, J.cell_start[rb + lo0], J.cell_start[rb + lo0 + 1], qx, qy, qz, best);
+                if (hi0 < g.d0) scan_range_exact<KCAP>(J, J.cell_start[rb + hi0], J.cell_start[rb + hi0 + 1], qx, qy, qz, best);
+            }
+        }
+        const double e_lo0 = (lo0 <= 0) ? inf : q0 - (g.o0 + (double)lo0 * g.cell);
+        const double e_hi0 = (hi0 >= g.d0 - 1) ? inf : (g.o0 + (double)(hi0 + 1) * g.cell) - q0;
+        const double e_lo1 = (lo1 <= 0) ? inf : q1 - (g.o1 + (double)lo1 * g.cell);
+        const double e_hi1 = (hi1 >= g.d1 - 1) ? inf : (g.o1 + (double)(hi1 + 1) * g.cell) - q1;
+        double lb = fmin(fmin(e_lo0, e_hi0), fmin(e_lo1, e_hi1));
+        if (lb == inf) break;
+        lb = lb - g.slack;
+        if (lb > 0.0 && best.d[0] <= lb * lb) break;
+    }
+    return best.sum_sqrt_ascending();
+}
+
+// ---- fast path -------------------------------------------------------------------------------------
+// Phase 1: every candidate of the search square goes through a branch-free sorted-insertion network on
+//          fp32 keys (2 FMNMX per slot, all lanes active, no divergence): the k+1 smallest keys survive.
+// Phase 2: the square is rescanned and the candidates whose key is within the fp32 error band of the
+//          k-th key are collected (indices, shared memory, <= kListCap per query).  Every true member of
+//          the exact k-set is in that list (see DESIGN.md "k-NN exactness").
+// Phase 3: fp64 distances of the collected candidates, exact branch-free selection of the k smallest,
+//          sqrt and ascending sum -- the arithmetic of the oracle.
+// A query whose list overflows (massive ties) is redone by the fp64-keyed slow path.
+constexpr int kListCap = 16;
+constexpr float kKeyErr = 1.5e-6f;     // relative error bound of the fp32 squared distance
+
+template <int KS>
+struct FNet {
+    float d[KS];                         // ascending: d[0] smallest
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int p = 0; p < KS; ++p) d[p] = __int_as_float(0x7f800000);
+    }
+    __device__ __forceinline__ void feed(float v) {
+#pragma unroll
+        for (int p = 0; p < KS; ++p) { const float lo = fminf(d[p], v); v = fmaxf(d[p], v); d[p] = lo; }
+    }
+    __device__ __forceinline__ float get(int idx) const {     // d[idx] with a runtime index (unrolled select)
+        float r = d[0];
+#pragma unroll
+        for (int p = 1; p < KS; ++p) r = (p == idx) ? d[p] : r;
+        return r;
+    }
+};
+
+__device__ __forceinline__ float key_f32(const KnnJob& J, int j, float qx, float qy, float qz) {
+    const float fx = __ldg(J.sx + j) - qx, fy = __ldg(J.sy + j) - qy, fz = __ldg(J.sz + j) - qz;
+    return (fx * fx + fy * fy) + fz * fz;               // identical expression in phases 1 and 2
+}
+
+// visit the cells that square(r) adds to square(rold) (rold < 0: everything), row by row
+template <typename F>
+__device__ __forceinline__ void for_new_segments(const KnnJob& J, const GridRt& g, int c0, int c1, int r, int rold, F&& f) {
+    const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
+    const int cl0 = max(lo0, 0), ch0 = min(hi0, g.d0 - 1);
+    for (int row = max(lo1, 0); row <= min(hi1, g.d1 - 1); ++row) {
+        const int rb = row * g.d0;
+        if (rold < 0 || row < c1 - rold || row > c1 + rold) {
+            f(J.cell_start[rb + cl0], J.cell_start[rb + ch0 + 1]);
+        } else {
+            const int le = min(c0 - rold - 1, ch0), rs = max(c0 + rold + 1, cl0);
+            if (le >= cl0) f(J.cell_start[rb + cl0], J.cell_start[rb + le + 1]);
+            if (rs <= ch0) f(J.cell_start[rb + rs], J.cell_start[rb + ch0 + 1]);
+        }
+    }
+}
+
+template <int KS>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(const KnnJob* __restrict__ jobs) {
-    __shared__ int s_last;
+    constexpr int K = KS - 1;
+    __shared__ int s_list[kListCap][kKnnThreads];
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const int keff = min(J.k, g.n);
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const int tid = threadIdx.x;
     U128 acc_sum{0ull, 0ull}, acc_sq{0ull, 0ull};
     unsigned long long acc_pos = 0ull;
 
-    for (int i = blockIdx.x * kKnnThreads + threadIdx.x; i < g.n; i += gridDim.x * kKnnThreads) {
+    for (int i = blockIdx.x * kKnnThreads + tid; i < g.n; i += gridDim.x * kKnnThreads) {
         const float qx = __ldg(J.sx + i), qy = __ldg(J.sy + i), qz = __ldg(J.sz + i);
         const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
         const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1);
-        Best<KCAP> best; best.init(keff);
-        float worst32 = __int_as_float(0x7f800000);
-        for (int r = 0;; ++r) {
+        // ---- phase 1
+        FNet<KS> net; net.init();
+        int rold = -1, r = 1;
+        for (;; r <<= 1) {
+            for_new_segments(J, g, c0, c1, r, rold, [&](int s, int e) {
+                for (int j = s; j < e; ++j) net.feed(key_f32(J, j, qx, qy, qz));
+            });
             const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
-            const int cl0 = max(lo0, 0), ch0 = min(hi0, g.d0 - 1);
-            for (int row = max(lo1, 0); row <= min(hi1, g.d1 - 1); ++row) {
-                const int rb = row * g.d0;
-                if (row == lo1 || row == hi1) {
-                    scan_range<KCAP>(J, J.cell_start[rb + cl0], J.cell_start[rb + ch0 + 1], qx, qy, qz, best, worst32);
-                } else {
-                    if (lo0 >= 0) scan_range<KCAP>(J, J.cell_start[rb + lo0], J.cell_start[rb + lo0 + 1], qx, qy, qz, best, worst32);
-                    if (hi0 < g.d0) scan_range<KCAP>(J, J.cell_start[rb + hi0], J.cell_start[rb + hi0 + 1], qx, qy, qz, best, worst32);
-                }
-            }
-            // every unvisited point lies outside the (2r+1)^2 square: lower-bound its distance
             const double e_lo0 = (lo0 <= 0) ? inf : q0 - (g.o0 + (double)lo0 * g.cell);
             const double e_hi0 = (hi0 >= g.d0 - 1) ? inf : (g.o0 + (double)(hi0 + 1) * g.cell) - q0;
             const double e_lo1 = (lo1 <= 0) ? inf : q1 - (g.o1 + (double)lo1 * g.cell);
@@ -289,42 +319,76 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
             double lb = fmin(fmin(e_lo0, e_hi0), fmin(e_lo1, e_hi1));
             if (lb == inf) break;                       // the square covers the whole grid
             lb = lb - g.slack;
-            if (lb > 0.0 && best.d[0] <= lb * lb) break;
+            // every unvisited point is at least lb away: stop when the k-th key (inflated by its error) is closer
+            if (lb > 0.0 && keff > 0 && (double)net.get(keff - 1) * 1.000002 <= lb * lb) break;
+            rold = r;
         }
-        const double avg = (keff > 0) ? best.sum_sqrt_ascending() / (double)keff : -1.0;
+        // ---- phase 2
+        const float wk = (keff > 0) ? net.get(keff - 1) : 0.f;
+        const float band = wk * (1.0f + 4.0f * kKeyErr);
+        int cnt = 0;
+        for_new_segments(J, g, c0, c1, r, -1, [&](int s, int e) {
+            for (int j = s; j < e; ++j) {
+                const bool in = key_f32(J, j, qx, qy, qz) <= band;
+                if (in && cnt < kListCap) s_list[cnt][tid] = j;
+                cnt += in ? 1 : 0;
+            }
+        });
+        // ---- phase 3
+        double sum;
+        if (cnt > kListCap || cnt < keff) {
+            sum = knn_exact_sum<(K > 0 ? K : 1)>(J, g, qx, qy, qz, q0, q1, c0, c1, keff);
+        } else {
+            double bd[K > 0 ? K : 1];
+#pragma unroll
+            for (int p = 0; p < K; ++p) bd[p] = inf;
+            for (int e = 0; e < cnt; ++e) {
+                const int j = s_list[e][tid];
+                const double dx = (double)__ldg(J.sx + j) - (double)qx, dy = (double)__ldg(J.sy + j) - (double)qy,
+                             dz = (double)__ldg(J.sz + j) - (double)qz;
+                double v = (dx * dx + dy * dy) + dz * dz;
+#pragma unroll
+                for (int p = 0; p < K; ++p) { const double lo = fmin(bd[p], v); v = fmax(bd[p], v); bd[p] = lo; }
+            }
+            sum = 0.0;
+#pragma unroll
+            for (int p = 0; p < K; ++p) if (p < keff) sum = sum + sqrt(bd[p]);
+        }
+        const double avg = (keff > 0) ? sum / (double)keff : -1.0;
         J.avg[__ldg(J.sorig + i)] = avg;
         J.savg[i] = avg;
         if (avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
     }
 
-    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums
+    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums.
+    //      Warps retire independently (no CTA barrier): the last WARP of the job finalises.
     acc_sum = warp_sum128(acc_sum); acc_sq = warp_sum128(acc_sq);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc_pos += __shfl_xor_sync(SD_FULL, acc_pos, o);
-    if (lane_id() == 0 && acc_pos) {
-        atomic_add128(J.gs->acc[0], acc_sum); atomic_add128(J.gs->acc[1], acc_sq);
-        atomicAdd(&J.gs->acc[2][0], acc_pos);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(&J.gs->ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (threadIdx.x == 0) {
-        GridState* gs = J.gs;
-        const double S = fixed70_to_double(__ldcg(&gs->acc[0][0]), __ldcg(&gs->acc[0][1]));
-        const double Q = fixed70_to_double(__ldcg(&gs->acc[1][0]), __ldcg(&gs->acc[1][1]));
-        const double Pn = (double)__ldcg(&gs->acc[2][0]);
-        gs->acc[0][0] = gs->acc[0][1] = gs->acc[1][0] = gs->acc[1][1] = gs->acc[2][0] = gs->acc[2][1] = 0ull;
-        const double n = (double)g.n;
-        const double mean = (g.n > 0) ? S / n : 0.0;
-        // sum over avg>0 of (avg-mean)^2 = Q - 2*mean*S + Pn*mean^2
-        double sq = (Q - 2.0 * mean * S) + Pn * mean * mean;
-        if (sq < 0.0) sq = 0.0;
-        const double sd_ = (g.n > 1) ? sqrt(sq / (n - 1.0)) : __longlong_as_double(0x7ff8000000000000ull);
-        J.stats[0] = mean; J.stats[1] = sd_; J.stats[2] = mean + J.std_ratio * sd_;
-        J.gs->ticket = 0;
+    int last = 0;
+    if (lane_id() == 0) {
+        if (acc_pos) {
+            atomic_add128(J.gs->acc[0], acc_sum); atomic_add128(J.gs->acc[1], acc_sq);
+            atomicAdd(&J.gs->acc[2][0], acc_pos);
+        }
+        __threadfence();
+        last = (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * (kKnnThreads / 32) - 1);
+        if (last) {
+            __threadfence();
+            GridState* gs = J.gs;
+            const double S = fixed70_to_double(__ldcg(&gs->acc[0][0]), __ldcg(&gs->acc[0][1]));
+            const double Q = fixed70_to_double(__ldcg(&gs->acc[1][0]), __ldcg(&gs->acc[1][1]));
+            const double Pn = (double)__ldcg(&gs->acc[2][0]);
+            gs->acc[0][0] = gs->acc[0][1] = gs->acc[1][0] = gs->acc[1][1] = gs->acc[2][0] = gs->acc[2][1] = 0ull;
+            const double n = (double)g.n;
+            const double mean = (g.n > 0) ? S / n : 0.0;
+            // sum over avg>0 of (avg-mean)^2 = Q - 2*mean*S + Pn*mean^2
+            double sq = (Q - 2.0 * mean * S) + Pn * mean * mean;
+            if (sq < 0.0) sq = 0.0;
+            const double sd_ = (g.n > 1) ? sqrt(sq / (n - 1.0)) : __longlong_as_double(0x7ff8000000000000ull);
+            J.stats[0] = mean; J.stats[1] = sd_; J.stats[2] = mean + J.std_ratio * sd_;
+            gs->ticket = 0;
+        }
     }
 }
 
@@ -336,6 +400,7 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const double r = J.radius, r2 = r * r;
+    const float r2_in = __double2float_rd(r2 * (1.0 - 3e-6)), r2_out = __double2float_ru(r2 * (1.0 + 3e-6));
     const bool sor = J.use_sor != 0;
     const double thr = sor ? J.stats[2] : 0.0;
     const int cap = J.count_cap;
@@ -367,15 +432,31 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
             const int ca = cell_coord(q0 - half, g.o0, g.inv_cell, g.d0), cb = cell_coord(q0 + half, g.o0, g.inv_cell, g.d0);
             const int rb = row * g.d0;
             const int s = J.cell_start[rb + ca], e = J.cell_start[rb + cb + 1];
-            for (int j = s; j < e; ++j) {
-                if (sor) { const double a = J.savg[j]; if (!(a > 0.0 && a < thr)) continue; }
+            // walk outwards from the query's own position (its own index in its row, the cell straight
+            // above / below it in the other rows): near candidates first, so dense queries stop after ~cap tests
+            const int c0q = cell_coord(q0, g.o0, g.inv_cell, g.d0);
+            int mid = (dr == 0) ? i : J.cell_start[rb + c0q];
+            mid = min(max(mid, s), e);
+            auto test = [&](int j) {
                 const float px = __ldg(J.sx + j), py = __ldg(J.sy + j), pz = __ldg(J.sz + j);
-                const double dx = (double)px - (double)qx, dy = (double)py - (double)qy, dz = (double)pz - (double)qz;
-                const double d2 = (dx * dx + dy * dy) + dz * dz;
-                if (d2 <= r2) {
-                    ++count;
-                    if (cap >= 0 && count > cap) { done = true; break; }
+                const float fx = px - qx, fy = py - qy, fz = pz - qz;
+                const float d2f = (fx * fx + fy * fy) + fz * fz;       // fp32 pre-test, relative error < 1.5e-6
+                if (d2f > r2_out) return;
+                bool in = d2f < r2_in;
+                if (!in) {
+                    const double dx = (double)px - (double)qx, dy = (double)py - (double)qy, dz = (double)pz - (double)qz;
+                    in = ((dx * dx + dy * dy) + dz * dz) <= r2;
                 }
+                if (in && sor) { const double a = J.savg[j]; in = (a > 0.0 && a < thr); }
+                if (in) {
+                    ++count;
+                    if (cap >= 0 && count > cap) done = true;
+                }
+            };
+            int jl = mid - 1, jr = mid;
+            while (!done && (jl >= s || jr < e)) {
+                if (jr < e) { test(jr); ++jr; }
+                if (!done && jl >= s) { test(jl); --jl; }
             }
         }
         J.cnt[orig] = count;
@@ -413,13 +494,13 @@ int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStrea
     if (njobs <= 0) return SD_OK;
     if (k < 1 || k > kMaxKnnK) return SD_ERR_INVALID;
     dim3 grid = grid_for(cap, kKnnThreads, 1, njobs, 16);   // <= kKnnMaxBlocks CTAs per job
-    if (k <= 4) knn_kernel<4><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 8) knn_kernel<8><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 10) knn_kernel<10><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 16) knn_kernel<16><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 20) knn_kernel<20><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 32) knn_kernel<32><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else knn_kernel<64><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    if (k <= 3) knn_kernel<4><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else if (k <= 7) knn_kernel<8><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else if (k <= 10) knn_kernel<11><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else if (k <= 16) knn_kernel<17><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else if (k <= 20) knn_kernel<21><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else if (k <= 32) knn_kernel<33><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    else knn_kernel<65><<<grid, kKnnThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

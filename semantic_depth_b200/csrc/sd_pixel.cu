@@ -8,11 +8,14 @@
 //   z cut       remove_from_to(road, 2, 0, 7)           semantic_depth.py:206, pcl.py:35-37
 //
 // HBM-bound: 20 B/pixel in (12 B logits + 2 x 4 B disparity), 16 B per surviving point out.
-// A CTA owns a tile of 1024 consecutive pixels.  The logits tile (12 KB, AoS) is staged in shared
-// memory by one TMA bulk copy (cp.async.bulk + mbarrier) so HBM sees full 128 B lines; disparities
-// are read as 128-bit vectors (the flipped map mirrored).  Per-class stable compaction = warp
-// shuffles + block scan + decoupled look-back over dynamically ticketed tiles: output order is the
-// raster order NumPy boolean indexing produces, and the source pixel index of every point is kept.
+// Three streaming kernels without any dependency between CTAs:
+//   pixel_label_kernel    a CTA owns 1024 consecutive pixels; its logits (12 KB, AoS) arrive in shared
+//                         memory through one TMA bulk copy (cp.async.bulk + mbarrier) so HBM sees full
+//                         lines, disparities are 128-bit loads (the flipped map mirrored); it decides the
+//                         labels and the road z cut and writes 1 flag byte per pixel + per-tile counts
+//   pixel_scan_kernel     exclusive scan of the tile counts of a frame (raster order = NumPy order)
+//   pixel_scatter_kernel  blends / reprojects the kept pixels again (cheaper than storing them) and writes
+//                         them at their final raster-ordered position, with their source pixel index
 #include "sd_internal.cuh"
 
 namespace sd {
@@ -83,108 +86,157 @@ struct PixArgs {
     SdCloudBuf road, fence; int cap_stride;
     int32_t* cnt_road_gather; int32_t* cnt_road_z; int32_t* cnt_fence; int cnt_stride;
     uint8_t* labels; float* points; float* disp_pp;
-    unsigned long long* status; ScanCtl* ctl; int pix_tiles;
+    uint8_t* flags;            // [B][hw]   bit0 road, bit1 fence, bit2 road point that survives the z cut
+    int32_t* tcounts;          // [B][tiles][4] per-tile counts: road (all), road kept, fence, -
+    int32_t* toffs;            // [B][tiles][2] exclusive offsets of the tile's road / fence points
+    int pix_tiles;
 };
 
+// blended + scaled disparity of one pixel (semantic_depth.py:660-664,676 and :145)
+__device__ __forceinline__ float blend_px(const PixArgs& a, float l, float r, int u, float& dpp) {
+    const float m = 0.5f * (l + r);
+    const double lm = __ldg(a.lmask + u), rm = __ldg(a.rmask + u);
+    if (a.raw_disp) {
+        dpp = l;
+    } else if (lm == 0.0 && rm == 0.0 && isfinite(m) && m != 0.0f) {
+        dpp = m;                                // (0*l + 0*r) + (1-0-0)*m == m exactly
+    } else {
+        const double t = (rm * (double)l + lm * (double)r) + ((1.0 - lm) - rm) * (double)m;
+        dpp = (float)t;
+    }
+    return a.raw_disp ? dpp : dpp * a.mult;     // fp32 product
+}
+
+__device__ __forceinline__ void load_disp4(const PixArgs& a, int f, int p, int v, int u0, float* l4, float* r4) {
+    const float* dl = a.disp + (size_t)f * 2 * a.hw;
+    const float* dr = dl + a.hw;
+    const float4 L = __ldg(reinterpret_cast<const float4*>(dl + p));
+    const float4 R = __ldg(reinterpret_cast<const float4*>(dr + (size_t)v * a.width + (a.width - 4 - u0)));
+    l4[0] = L.x; l4[1] = L.y; l4[2] = L.z; l4[3] = L.w;
+    r4[0] = R.w; r4[1] = R.z; r4[2] = R.y; r4[3] = R.x;   // np.fliplr of the second map
+}
+
+// ---- kernel 1: labels + z cut -> 1 byte per pixel and per-tile counts.  Pure streaming: every CTA is
+//      independent (no scan, no look-back), 20 B read and 1 B written per pixel.
 __global__ void __launch_bounds__(kPixThreads)
-pixel_fuse_kernel(const __grid_constant__ PixArgs a) {
+pixel_label_kernel(const __grid_constant__ PixArgs a) {
     __shared__ __align__(128) float s_logits[kPixTile * 3];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_scan[33];
-    __shared__ int s_tile;
-    __shared__ unsigned long long s_excl;
-
-    const int f = blockIdx.y;
-    const int tid = threadIdx.x;
-    ScanCtl* ctl = a.ctl + f;
-    unsigned long long* status = a.status + (size_t)f * a.pix_tiles;
-
-    if (tid == 0) {
-        s_tile = (int)atomicAdd(&ctl->ticket, 1u);
-        mbar_init(&s_bar, 1);
-    }
-    __syncthreads();
-    const int tile = s_tile;
+    __shared__ int s_cnt[kPixThreads / 32][3];
+    const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int pix0 = tile * kPixTile;
     const int npix = min(kPixTile, a.hw - pix0);
-
     if (tid == 0) {
-        uint32_t bytes = (uint32_t)npix * 12u;
+        mbar_init(&s_bar, 1);
+        const uint32_t bytes = (uint32_t)npix * 12u;
         mbar_expect_tx(&s_bar, bytes);
         tma_bulk_g2s(s_logits, a.logits + ((size_t)f * a.hw + pix0) * 3, bytes, &s_bar);
     }
-
-    const int p = pix0 + tid * kPixPer;           // first pixel of this thread (flat, in frame)
+    __syncthreads();
+    const int p = pix0 + tid * kPixPer;
     const bool active = p < a.hw;
     float l4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {0.f, 0.f, 0.f, 0.f};
     int v = 0, u0 = 0;
-    if (active) {
-        v = p / a.width;
-        u0 = p - v * a.width;
-        const float* dl = a.disp + (size_t)f * 2 * a.hw;
-        const float* dr = dl + a.hw;
-        float4 L = __ldg(reinterpret_cast<const float4*>(dl + p));
-        float4 R = __ldg(reinterpret_cast<const float4*>(dr + (size_t)v * a.width + (a.width - 4 - u0)));
-        l4[0] = L.x; l4[1] = L.y; l4[2] = L.z; l4[3] = L.w;
-        r4[0] = R.w; r4[1] = R.z; r4[2] = R.y; r4[3] = R.x;   // np.fliplr of the second map
-    }
+    if (active) { v = p / a.width; u0 = p - v * a.width; load_disp4(a, f, p, v, u0, l4, r4); }
     mbar_wait(&s_bar, 0);
-
-    const double q0 = (double)a.q03, q1 = (double)a.q13, q2 = (double)a.q23, q3 = (double)a.q32;
+    const double q2 = (double)a.q23, q3 = (double)a.q32;
     const float thr32 = (float)a.thr;
-    float X[4], Y[4], Z[4], D[4];
-    int lab[4];
     int n_road = 0, n_roadz = 0, n_fence = 0;
-    bool keep_road[4], keep_fence[4];
-    const bool want_all = (a.points != nullptr);
-    const double yh = q1 - (double)v;              // -1*v + cy   (row 1 of Q)
-#pragma unroll
-    for (int j = 0; j < kPixPer; ++j) {
-        keep_road[j] = keep_fence[j] = false;
-        lab[j] = 0;
-        X[j] = Y[j] = Z[j] = D[j] = 0.f;
-        if (!active) continue;
-        const int u = u0 + j;
-        const float* lg = s_logits + (tid * kPixPer + j) * 3;
-        lab[j] = classify(lg[0], lg[1], lg[2], a.thr, thr32);
-        // ---- blend (semantic_depth.py:660-664): m is fp32, the ramps are fp64
-        const float l = l4[j], r = r4[j];
-        const float m = 0.5f * (l + r);
-        const double lm = __ldg(a.lmask + u), rm = __ldg(a.rmask + u);
-        float dpp;
-        if (a.raw_disp) {
-            dpp = l;
-        } else if (lm == 0.0 && rm == 0.0 && isfinite(m) && m != 0.0f) {
-            dpp = m;                                // (0*l + 0*r) + (1-0-0)*m == m exactly
-        } else {
-            double t = (rm * (double)l + lm * (double)r) + ((1.0 - lm) - rm) * (double)m;
-            dpp = (float)t;
-        }
-        D[j] = dpp;
-        if (lab[j] != 0 || want_all) {
-            const float d = a.raw_disp ? dpp : dpp * a.mult;   // semantic_depth.py:145 (fp32 product)
-            const double wp = q3 * (double)d;       // W = Q[3][2]*d
-            const double rwp = 1.0 / wp;
-            const double xh = (double)u + q0;       // 1*u - cx
-            X[j] = div_to_f32(xh, rwp, wp);
-            Y[j] = div_to_f32(yh, rwp, wp);
-            Z[j] = div_to_f32(q2, rwp, wp);
-        }
-        if (lab[j] & 1) {
-            ++n_road;
-            keep_road[j] = Z[j] < -a.road_z_cut;    // pcl.py:36
-            n_roadz += keep_road[j] ? 1 : 0;
-        }
-        if (lab[j] & 2) { keep_fence[j] = true; ++n_fence; }
-    }
-
-    // ---- optional dense outputs (parity tests / facade): labels, points3D, blended disparity
+    unsigned char fl[4] = {0, 0, 0, 0};
     if (active) {
-        const size_t gp = (size_t)f * a.hw + p;
-        if (a.labels) {
-            uchar4 lb = make_uchar4((unsigned char)lab[0], (unsigned char)lab[1], (unsigned char)lab[2], (unsigned char)lab[3]);
-            *reinterpret_cast<uchar4*>(a.labels + gp) = lb;
+#pragma unroll
+        for (int j = 0; j < kPixPer; ++j) {
+            const float* lg = s_logits + (tid * kPixPer + j) * 3;
+            int lab = classify(lg[0], lg[1], lg[2], a.thr, thr32);
+            if (lab & 1) {
+                float dpp;
+                const float d = blend_px(a, l4[j], r4[j], u0 + j, dpp);
+                const double wp = q3 * (double)d;
+                const float z = div_to_f32(q2, 1.0 / wp, wp);
+                ++n_road;
+                if (z < -a.road_z_cut) { lab |= 4; ++n_roadz; }          // pcl.py:36
+            }
+            n_fence += (lab & 2) ? 1 : 0;
+            fl[j] = (unsigned char)lab;
         }
+        *reinterpret_cast<uchar4*>(a.flags + (size_t)f * a.hw + p) = make_uchar4(fl[0], fl[1], fl[2], fl[3]);
+        if (a.labels) *reinterpret_cast<uchar4*>(a.labels + (size_t)f * a.hw + p) = make_uchar4(fl[0] & 3, fl[1] & 3, fl[2] & 3, fl[3] & 3);
+    }
+    n_road = warp_sum(n_road); n_roadz = warp_sum(n_roadz); n_fence = warp_sum(n_fence);
+    if (lane_id() == 0) { s_cnt[warp_id()][0] = n_road; s_cnt[warp_id()][1] = n_roadz; s_cnt[warp_id()][2] = n_fence; }
+    __syncthreads();
+    if (tid < 3) {
+        int t = 0;
+        for (int w = 0; w < kPixThreads / 32; ++w) t += s_cnt[w][tid];
+        a.tcounts[((size_t)f * a.pix_tiles + tile) * 4 + tid] = t;
+    }
+}
+
+// ---- kernel 2: exclusive scan of the tile counts of each frame (one CTA per frame)
+__global__ void __launch_bounds__(1024)
+pixel_scan_kernel(const __grid_constant__ PixArgs a) {
+    __shared__ int s_scan[33];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    const int32_t* tc = a.tcounts + (size_t)f * a.pix_tiles * 4;
+    int32_t* to = a.toffs + (size_t)f * a.pix_tiles * 2;
+    int run_road = 0, run_fence = 0, all_road = 0;
+    for (int base = 0; base < a.pix_tiles; base += 1024) {
+        const int t = base + tid;
+        int cr = 0, cf = 0, ca = 0;
+        if (t < a.pix_tiles) { ca = tc[t * 4]; cr = tc[t * 4 + 1]; cf = tc[t * 4 + 2]; }
+        int tot_r, tot_f, tot_a;
+        const int er = block_excl_scan(cr, s_scan, &tot_r);
+        const int ef = block_excl_scan(cf, s_scan, &tot_f);
+        block_excl_scan(ca, s_scan, &tot_a);
+        if (t < a.pix_tiles) { to[t * 2] = run_road + er; to[t * 2 + 1] = run_fence + ef; }
+        run_road += tot_r; run_fence += tot_f; all_road += tot_a;
+    }
+    if (tid == 0) {
+        a.cnt_road_gather[(size_t)f * a.cnt_stride] = all_road;
+        a.cnt_road_z[(size_t)f * a.cnt_stride] = run_road;
+        a.cnt_fence[(size_t)f * a.cnt_stride] = run_fence;
+    }
+}
+
+// ---- kernel 3: blend + reprojection of the kept pixels and their raster-ordered scatter
+__global__ void __launch_bounds__(kPixThreads)
+pixel_scatter_kernel(const __grid_constant__ PixArgs a) {
+    __shared__ int s_scan[33];
+    const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
+    const bool want_all = (a.points != nullptr) || (a.disp_pp != nullptr);
+    const int32_t* tc = a.tcounts + ((size_t)f * a.pix_tiles + tile) * 4;
+    if (!want_all && tc[1] == 0 && tc[2] == 0) return;          // nothing of this tile survives (sky)
+    const int p = tile * kPixTile + tid * kPixPer;
+    const bool active = p < a.hw;
+    const double q0 = (double)a.q03, q1 = (double)a.q13, q2 = (double)a.q23, q3 = (double)a.q32;
+    float X[4], Y[4], Z[4], D[4];
+    unsigned char fl[4] = {0, 0, 0, 0};
+    int n_roadz = 0, n_fence = 0;
+    if (active) {
+        const uchar4 fb = *reinterpret_cast<const uchar4*>(a.flags + (size_t)f * a.hw + p);
+        fl[0] = fb.x; fl[1] = fb.y; fl[2] = fb.z; fl[3] = fb.w;
+    }
+    const bool any = want_all || ((fl[0] | fl[1] | fl[2] | fl[3]) & 6);
+    if (active && any) {
+        const int v = p / a.width, u0 = p - v * a.width;
+        float l4[4], r4[4];
+        load_disp4(a, f, p, v, u0, l4, r4);
+        const double yh = q1 - (double)v;              // -1*v + cy   (row 1 of Q)
+#pragma unroll
+        for (int j = 0; j < kPixPer; ++j) {
+            X[j] = Y[j] = Z[j] = D[j] = 0.f;
+            if (want_all || (fl[j] & 6)) {
+                const float d = blend_px(a, l4[j], r4[j], u0 + j, D[j]);
+                const double wp = q3 * (double)d;       // W = Q[3][2]*d
+                const double rwp = 1.0 / wp;
+                X[j] = div_to_f32((double)(u0 + j) + q0, rwp, wp);
+                Y[j] = div_to_f32(yh, rwp, wp);
+                Z[j] = div_to_f32(q2, rwp, wp);
+            }
+            n_roadz += (fl[j] & 4) ? 1 : 0;
+            n_fence += (fl[j] & 2) ? 1 : 0;
+        }
+        const size_t gp = (size_t)f * a.hw + p;
         if (a.disp_pp) *reinterpret_cast<float4*>(a.disp_pp + gp) = make_float4(D[0], D[1], D[2], D[3]);
         if (a.points) {
             float4* o = reinterpret_cast<float4*>(a.points + gp * 3);
@@ -193,46 +245,22 @@ pixel_fuse_kernel(const __grid_constant__ PixArgs a) {
             o[2] = make_float4(Z[2], X[3], Y[3], Z[3]);
         }
     }
-
-    // ---- stable compaction of both classes: block scan of packed counts + look-back across tiles
     int total;
-    const int packed = n_roadz | (n_fence << 16);
-    const int excl = block_excl_scan(packed, s_scan, &total);
-    // block total of *all* road pixels (count only, no ordering needed)
-    int ra = warp_sum(n_road);
-    if (lane_id() == 0 && ra) atomicAdd(&ctl->aux0, (unsigned)ra);
-
-    if (warp_id() == 0) {
-        unsigned long long agg = (unsigned long long)(total & 0xffff) | ((unsigned long long)(total >> 16) << 31);
-        unsigned long long e = lookback_exclusive(status, tile, agg);
-        if (lane_id() == 0) s_excl = e;
-    }
-    __syncthreads();
-    const unsigned long long ex = s_excl;
-    int road_pos = (int)(ex & 0x7fffffffull) + (excl & 0xffff);
-    int fence_pos = (int)((ex >> 31) & 0x7fffffffull) + (excl >> 16);
+    const int excl = block_excl_scan(n_roadz | (n_fence << 16), s_scan, &total);
+    const int32_t* to = a.toffs + ((size_t)f * a.pix_tiles + tile) * 2;
+    int road_pos = to[0] + (excl & 0xffff), fence_pos = to[1] + (excl >> 16);
     const size_t cb = (size_t)f * a.cap_stride;
 #pragma unroll
     for (int j = 0; j < kPixPer; ++j) {
-        if (keep_road[j]) {
+        if (fl[j] & 4) {
             a.road.x[cb + road_pos] = X[j]; a.road.y[cb + road_pos] = Y[j]; a.road.z[cb + road_pos] = Z[j];
             a.road.src[cb + road_pos] = p + j;
             ++road_pos;
         }
-        if (keep_fence[j]) {
+        if (fl[j] & 2) {
             a.fence.x[cb + fence_pos] = X[j]; a.fence.y[cb + fence_pos] = Y[j]; a.fence.z[cb + fence_pos] = Z[j];
             a.fence.src[cb + fence_pos] = p + j;
             ++fence_pos;
-        }
-    }
-    if (tile == a.pix_tiles - 1 && tid == 0) {
-        a.cnt_road_z[(size_t)f * a.cnt_stride] = (int)(ex & 0x7fffffffull) + (total & 0xffff);
-        a.cnt_fence[(size_t)f * a.cnt_stride] = (int)((ex >> 31) & 0x7fffffffull) + (total >> 16);
-    }
-    // ---- last block of the frame: publish the road_gather count, clean the look-back words
-    if (scan_finish(ctl, status, a.pix_tiles, a.pix_tiles)) {
-        if (tid == 0) {
-            a.cnt_road_gather[(size_t)f * a.cnt_stride] = (int)atomicExch(&ctl->aux0, 0u);
         }
     }
 }
@@ -244,7 +272,7 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
                     SdCloudBuf road, SdCloudBuf fence, int cap_stride,
                     int32_t* d_cnt_road_gather, int32_t* d_cnt_road_z, int32_t* d_cnt_fence, int cnt_stride,
                     uint8_t* d_labels, float* d_points, float* d_disp_pp,
-                    unsigned long long* status, sd::ScanCtl* ctl, int pix_tiles, cudaStream_t st) {
+                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st) {
     using namespace sd;
     if (width % 4 != 0 || width < 4 || height < 1 || batch < 1) return SD_ERR_INVALID;
     PixArgs a;
@@ -256,9 +284,11 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
     a.cnt_road_gather = d_cnt_road_gather; a.cnt_road_z = d_cnt_road_z; a.cnt_fence = d_cnt_fence;
     a.cnt_stride = cnt_stride;
     a.labels = d_labels; a.points = d_points; a.disp_pp = d_disp_pp;
-    a.status = status; a.ctl = ctl; a.pix_tiles = pix_tiles;
+    a.flags = d_flags; a.tcounts = d_tcounts; a.toffs = d_toffs; a.pix_tiles = pix_tiles;
     dim3 grid(pix_tiles, batch);
-    pixel_fuse_kernel<<<grid, kPixThreads, 0, st>>>(a);
+    pixel_label_kernel<<<grid, kPixThreads, 0, st>>>(a);
+    pixel_scan_kernel<<<batch, 1024, 0, st>>>(a);
+    pixel_scatter_kernel<<<grid, kPixThreads, 0, st>>>(a);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

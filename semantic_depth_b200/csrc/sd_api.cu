@@ -112,6 +112,7 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->sel = c.take<SelState>((size_t)F * kChains);
     ws->cstatus = c.take<unsigned long long>((size_t)F * kChains * ws->max_tiles);
     ws->cctl = c.take<ScanCtl>((size_t)F * kChains);
+    ws->mean_leaf = c.take<float>((size_t)F * (cap / 64 + 1));
     ws->partials = c.take<double>((size_t)F * kChains * kPlaneBlocks * kPlaneSums);
     ws->ptick = c.take<uint32_t>((size_t)F * kChains);
     ws->pflags = c.take<uint8_t>((size_t)F * ws->height * ws->width);
@@ -228,7 +229,7 @@ void fill_knn(KnnJob& j, const float* x, const float* y, const float* z, const i
 }  // namespace
 
 extern "C" size_t sd_ws_bytes(int max_frames, int height, int width, int max_hypotheses) {
-    if (max_frames < 1 || height < 1 || width < 4) return 0;
+    if (max_frames < 1 || height < 1 || width < 4 || width % 4 != 0) return 0;
     SdWorkspace tmp; memset(&tmp, 0, sizeof(tmp));
     set_dims(&tmp, max_frames, height, width, max_hypotheses);
     Carver c{nullptr, 0, 0, true};
@@ -439,7 +440,7 @@ extern "C" int sd_mean_f32(const float* d_col, int n, float* h_mean, SdWorkspace
     CallScratch* cs = call_scratch(ws);
     MeanJob* dj = reinterpret_cast<MeanJob*>(call_jobs(ws));
     SD_CUDA_TRY(cudaMemcpyAsync(&cs->n_in, &n, sizeof(int), cudaMemcpyHostToDevice, st));
-    MeanJob j{d_col, &cs->n_in, &cs->f[2]};
+    MeanJob j{d_col, &cs->n_in, &cs->f[2], ws->mean_leaf};
     SD_CUDA_TRY(cudaMemcpyAsync(dj, &j, sizeof(j), cudaMemcpyHostToDevice, st));
     rc = sd_launch_mean(dj, 1, st); if (rc) return rc;
     return download_sync(h_mean, &cs->f[2], 1, ws, st);
@@ -637,7 +638,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
         { PredDev p = make_pred(SD_PRED_ABS_LT, 2); p.fa = P.fence_abs_z_thr;
           fill_compact(h_c_fence_z[f], fB, &fs->n[SD_CNT_FENCE_MAD_Y], fA, &fs->n[SD_CNT_FENCE_ABS_Z], p, ws, f, 1); }
         // mean x and the split: fA -> lA, gA                               :286-287
-        h_m_fence[f] = MeanJob{fA.x, &fs->n[SD_CNT_FENCE_ABS_Z], &fs->fence_mean};
+        h_m_fence[f] = MeanJob{fA.x, &fs->n[SD_CNT_FENCE_ABS_Z], &fs->fence_mean, ws->mean_leaf + (size_t)f * (cap / 64 + 1)};
         { PredDev p = make_pred(SD_PRED_LT, 0); p.p_f0 = &fs->fence_mean;
           fill_compact(h_c_split[2 * f], fA, &fs->n[SD_CNT_FENCE_ABS_Z], lA, &fs->n[SD_CNT_LEFT_SPLIT], p, ws, f, 2); }
         { PredDev p = make_pred(SD_PRED_GT, 0); p.p_f0 = &fs->fence_mean;

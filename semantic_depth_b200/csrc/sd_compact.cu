@@ -183,36 +183,25 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
 constexpr int kMeanDepth = 10;
 constexpr int kMeanThreads = 1 << kMeanDepth;
 
-__device__ float pairwise_leaf(const float* a, int n) {     // n <= 128
-    if (n < 8) {
-        float r = 0.f;
-        for (int i = 0; i < n; ++i) r = r + a[i];
-        return r;
+// leaf of the pairwise tree that contains element e
+__device__ __forceinline__ void find_leaf(int n, int e, int& off, int& len) {
+    off = 0; len = n;
+    while (len > 128) {
+        int n2 = len / 2; n2 -= n2 % 8;
+        if (e < off + n2) len = n2; else { off += n2; len -= n2; }
     }
-    float r[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = a[j];
-    int i;
-    for (i = 8; i < n - (n % 8); i += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = r[j] + a[i + j];
-    }
-    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res = res + a[i];
-    return res;
 }
 
-// serial pairwise sum of an arbitrary range with an explicit stack (depth <= 24)
-__device__ float pairwise_serial(const float* a, int n) {
-    // iterative post-order evaluation
+// sum of the subtree (off, len) from the stored leaf sums, in NumPy's order (explicit stack, depth <= 24)
+__device__ float subtree_from_leaves(const float* leaf, int off0, int len0) {
     struct Fr { int off, n, state; float left; };
     Fr st[26];
     int sp = 0;
-    st[0] = {0, n, 0, 0.f};
+    st[0] = {off0, len0, 0, 0.f};
     float ret = 0.f;
     while (sp >= 0) {
         Fr& f = st[sp];
-        if (f.n <= 128) { ret = pairwise_leaf(a + f.off, f.n); --sp; continue; }
+        if (f.n <= 128) { ret = leaf[f.off >> 6]; --sp; continue; }
         int n2 = f.n / 2; n2 -= n2 % 8;
         if (f.state == 0) { f.state = 1; st[sp + 1] = {f.off, n2, 0, 0.f}; ++sp; }
         else if (f.state == 1) { f.left = ret; f.state = 2; st[sp + 1] = {f.off + n2, f.n - n2, 0, 0.f}; ++sp; }
@@ -225,7 +214,6 @@ __device__ float pairwise_serial(const float* a, int n) {
 // index among the nodes of its depth (bit string from the root); leaves that end early store their
 // value at the slot of their left-most descendant.
 __device__ float combine_levels(const float* vals, int n, int path, int levels, int stride_shift) {
-    // vals index of a node at relative depth d with relative path q: (q << (levels - d)) << stride_shift
     struct Fr { int n, q, d, state; float left; };
     Fr st[12];
     int sp = 0;
@@ -245,6 +233,12 @@ __device__ float combine_levels(const float* vals, int n, int path, int levels, 
     return ret;
 }
 
+// One CTA of 1024 threads per job.
+//   A. leaf sums: 8 lanes per leaf play NumPy's 8 strided accumulators (coalesced loads), combined as
+//      ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) by three xor-shuffles, then the n%8 tail; a leaf (>= 64
+//      elements whenever n > 128) is owned by the 64-element slot its start falls in
+//   B. thread t sums the leaf sums of the depth-10 subtree reached by the bits of t, in tree order
+//   C. 32 lanes combine levels 5..9, one lane levels 0..4; mean = fl32(sum / fl32(n))
 __global__ void __launch_bounds__(kMeanThreads)
 mean_kernel(const MeanJob* __restrict__ jobs) {
     __shared__ float s_sub[kMeanThreads];
@@ -252,20 +246,51 @@ mean_kernel(const MeanJob* __restrict__ jobs) {
     const MeanJob J = jobs[blockIdx.x];
     const int n = *J.n;
     const int t = threadIdx.x;
-    // descend kMeanDepth levels following the bits of t (MSB first)
+    const float* __restrict__ a = J.col;
+    // ---- A (the slot loop has the same trip count for every thread of the CTA)
+    const int grp = t >> 3, j = t & 7, ngroups = kMeanThreads >> 3;
+    const int nslots = (n + 63) >> 6;
+    if (n == 0 && t == 0) J.leaf[0] = 0.f;
+    for (int s0 = 0; s0 < nslots; s0 += ngroups) {
+        const int slot = s0 + grp;
+        int off = 0, len = 0;
+        bool owner = false;
+        if (slot < nslots) {
+            find_leaf(n, min(slot * 64 + 63, n - 1), off, len);
+            owner = (off >> 6) == slot;
+        }
+        float r = 0.f;
+        if (owner) {
+            if (len < 8) {
+                if (j == 0) for (int i = 0; i < len; ++i) r = r + a[off + i];
+            } else {
+                r = a[off + j];
+                const int body = len - (len % 8);
+                for (int i = 8; i < body; i += 8) r = r + a[off + i + j];
+            }
+        }
+        const float r1 = r + __shfl_xor_sync(SD_FULL, r, 1);
+        const float r2 = r1 + __shfl_xor_sync(SD_FULL, r1, 2);
+        const float r3 = r2 + __shfl_xor_sync(SD_FULL, r2, 4);
+        if (owner && j == 0) {
+            float res = (len < 8) ? r : r3;
+            if (len >= 8) for (int i = len - (len % 8); i < len; ++i) res = res + a[off + i];
+            J.leaf[slot] = res;
+        }
+    }
+    __syncthreads();
+    // ---- B: descend kMeanDepth levels following the bits of t (MSB first)
     int off = 0, len = n; bool owner = true; int d = 0;
     for (; d < kMeanDepth; ++d) {
         if (len <= 128) break;
         int n2 = len / 2; n2 -= n2 % 8;
         if ((t >> (kMeanDepth - 1 - d)) & 1) { off += n2; len -= n2; } else { len = n2; }
     }
-    if (d < kMeanDepth) {   // reached a leaf early: only the thread whose remaining bits are 0 owns it
-        owner = ((t & ((1 << (kMeanDepth - d)) - 1)) == 0);
-    }
-    s_sub[t] = owner ? pairwise_serial(J.col + off, len) : 0.f;
+    if (d < kMeanDepth) owner = ((t & ((1 << (kMeanDepth - d)) - 1)) == 0);
+    s_sub[t] = owner ? subtree_from_leaves(J.leaf, off, len) : 0.f;
     __syncthreads();
+    // ---- C
     if (t < 32) {
-        // node of lane t at depth 5: recompute its size
         int len5 = n; bool own5 = true; int d5 = 0;
         for (; d5 < 5; ++d5) {
             if (len5 <= 128) break;

@@ -97,6 +97,7 @@ struct PlaneJob {
 // ---- NumPy pairwise fp32 mean ----------------------------------------------------------------------------
 struct MeanJob {
     const float* col; const int32_t* n; float* out;
+    float* leaf;                // [cap/64 + 1] scratch: pairwise leaf sums, indexed by leaf_start / 64
 };
 
 // ---- slab min/max ---------------------------------------------------------------------------------------
@@ -119,6 +120,8 @@ struct GridState {
     double cell, inv_cell;
     double ext2;                // extent of the collapsed axis (for the 2D-inside shortcut)
     unsigned long long acc[3][2];  // exact 128-bit fixed-point sums of avg, avg^2 (lo, hi) and the count of avg > 0
+    int32_t work;                  // dynamic work counter of the search kernels (next unclaimed sorted index)
+    int32_t pad_;
 };
 struct KnnJob {
     const float* x; const float* y; const float* z; const int32_t* n;
@@ -248,6 +251,7 @@ struct SdWorkspace {
     sd::SelState* sel;                   // [F][4]
     unsigned long long* cstatus;         // [F][4][max_tiles]
     sd::ScanCtl* cctl;                   // [F][4]
+    float* mean_leaf;                    // [F][cap/64 + 1]
     double* partials;                    // [F][4][kPlaneBlocks*kPlaneSums]
     uint32_t* ptick;                     // [F][4]
     // pixel pass

@@ -300,7 +300,15 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
     U128 acc_sum{0ull, 0ull}, acc_sq{0ull, 0ull};
     unsigned long long acc_pos = 0ull;
 
-    for (int i = blockIdx.x * kKnnThreads + tid; i < g.n; i += gridDim.x * kKnnThreads) {
+    // warps claim 32 consecutive (cell-sorted) queries at a time from a per-job counter: sparse-region
+    // queries cost 10-100x more than dense ones, static partitioning left half of the SMs idle at the end
+    while (true) {
+        int wbase = 0;
+        if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
+        wbase = __shfl_sync(SD_FULL, wbase, 0);
+        if (wbase >= g.n) break;
+        const int i = wbase + lane_id();
+        if (i >= g.n) continue;
         const float qx = __ldg(J.sx + i), qy = __ldg(J.sy + i), qz = __ldg(J.sz + i);
         const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
         const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1);
@@ -387,7 +395,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
             if (sq < 0.0) sq = 0.0;
             const double sd_ = (g.n > 1) ? sqrt(sq / (n - 1.0)) : __longlong_as_double(0x7ff8000000000000ull);
             J.stats[0] = mean; J.stats[1] = sd_; J.stats[2] = mean + J.std_ratio * sd_;
-            gs->ticket = 0;
+            gs->ticket = 0; gs->work = 0;
         }
     }
 }
@@ -406,7 +414,13 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
     const int cap = J.count_cap;
     const int rows = (int)ceil(r * g.inv_cell) + 1;
     int alive_local = 0;
-    for (int i = blockIdx.x * kKnnThreads + threadIdx.x; i < g.n; i += gridDim.x * kKnnThreads) {
+    while (true) {
+        int wbase = 0;
+        if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
+        wbase = __shfl_sync(SD_FULL, wbase, 0);
+        if (wbase >= g.n) break;
+        const int i = wbase + lane_id();
+        if (i >= g.n) continue;
         const int orig = __ldg(J.sorig + i);
         if (sor) {
             const double a = J.savg[i];
@@ -461,9 +475,11 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
         }
         J.cnt[orig] = count;
     }
-    if (sor && J.n_alive) {
-        alive_local = warp_sum(alive_local);
-        if (lane_id() == 0 && alive_local) atomicAdd(J.n_alive, alive_local);
+    alive_local = warp_sum(alive_local);
+    if (lane_id() == 0) {
+        if (sor && J.n_alive && alive_local) atomicAdd(J.n_alive, alive_local);
+        __threadfence();
+        if (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * (kKnnThreads / 32) - 1) { J.gs->ticket = 0; J.gs->work = 0; }
     }
 }
 

@@ -1,0 +1,153 @@
+"""CPU suite: the C-ABI library loads and exports what include/sd_fusion.h declares, struct layouts match the
+ctypes mirror, the host-side logic (params, scene, sharding) behaves, and the product never imports the oracle.
+No compute call is made here (there is no GPU in this environment)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from semantic_depth_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from semantic_depth_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "sd_fusion.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t|void|const char\*)\s+(sd_\w+)\s*\(", header, flags=re.M))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in sd_fusion.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
+    assert lib.sd_abi_version() == 1
+
+
+def test_struct_layouts_and_defaults(lib):
+    from semantic_depth_b200 import _lib
+    from semantic_depth_b200.engine import RESULT_DTYPE, params_struct
+    from semantic_depth_b200.params import FusionParams
+    assert C.sizeof(_lib.SdFrameResult) == RESULT_DTYPE.itemsize == 328
+    assert C.sizeof(_lib.SdCamera) == 20 and C.sizeof(_lib.SdPredicate) == 72
+    p = _lib.SdParams()
+    lib.sd_default_params(C.byref(p), 10.0)
+    q = params_struct(FusionParams())
+    for name, _ in _lib.SdParams._fields_:
+        assert getattr(p, name) == getattr(q, name), name          # the C defaults == the reference literals
+    assert p.slab_lo == -((10.0 - 0.02) + 0.05) and p.slab_hi == -((10.0 - 0.02) - 0.05)
+    assert lib.sd_fuse_kernel_count(C.byref(p), 0) > 30
+    assert lib.sd_ws_bytes(1, 1024, 2048, 0) > 100 << 20 and lib.sd_ws_bytes(1, 8, 6, 0) == 0   # width % 4
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from semantic_depth_b200 import _lib
+    from semantic_depth_b200.engine import FusionEngine
+    with pytest.raises(_lib.SdError):
+        FusionEngine(64, 128)
+    import semantic_depth_lib.pcl as pcl
+    with pytest.raises((_lib.SdError, RuntimeError, AssertionError)):
+        pcl.remove_noise_by_mad(np.zeros((10, 3), np.float32), np.zeros((10, 3), np.uint8), 1, 15.0)
+
+
+def test_product_never_imports_the_oracle():
+    for pkg in ("semantic_depth_b200", "semantic_depth_lib"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{pkg}/{f} imports the oracle"
+    code = "import sys; import semantic_depth_b200, semantic_depth_lib.pcl, semantic_depth_b200.stream; print(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert out.stdout.strip() == "False", out.stdout + out.stderr
+
+
+def test_status_bits_agree_everywhere():
+    from oracle import frame_ref
+    from semantic_depth_b200 import params
+    header = open(os.path.join(ROOT, "include", "sd_fusion.h")).read()
+    for name in ("EMPTY_ROAD", "EMPTY_FENCE_LEFT", "EMPTY_FENCE_RIGHT", "MAD_ZERO", "NO_SLAB_POINTS", "SINGULAR_PLANES",
+                 "EMPTY_FENCE", "SINGULAR_FIT"):
+        shift = int(re.search(rf"SD_ST_{name} = 1 << (\d+)", header).group(1))
+        assert getattr(params, f"STATUS_{name}") == 1 << shift == getattr(frame_ref, name)
+    assert params.status_to_names(17) == ["EMPTY_ROAD", "NO_SLAB_POINTS"]
+
+
+def test_scene_is_deterministic_and_shaped():
+    from semantic_depth_b200 import scene
+    from semantic_depth_b200.params import Intrinsics
+    a = scene.make_frame(64, 128, 3)
+    b = scene.make_frame(64, 128, 3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert a[0].shape == (64 * 128, 3) and a[0].dtype == np.float32 and a[1].shape == (2, 64, 128)
+    assert not np.array_equal(a[0], scene.make_frame(64, 128, 4)[0])
+    label, depth = scene.scene_geometry(256, 512)
+    assert set(np.unique(label)) == {0, 1, 2} and depth.max() == 80.0 and depth.min() > 5.0
+    q = Intrinsics.cityscapes(512).as_q32()
+    assert q.dtype == np.float32 and q[2] == np.float32(-500.0) and q[3] == np.float32(1 / 0.6)
+    lg, dp, _ = scene.make_batch(2, 32, 64, first_seed=5)
+    assert np.array_equal(lg[1], scene.make_frame(32, 64, 6)[0])
+    cloud = scene.make_road_cloud(1000, seed=0)
+    assert cloud.shape == (1000, 3) and cloud.dtype == np.float32
+
+
+def test_shard_frames_partitions_exactly():
+    from semantic_depth_b200.stream import shard_frames
+    for n in (0, 1, 5, 600, 601, 607):
+        for world in (1, 2, 4, 8):
+            chunks = [shard_frames(n, r, world) for r in range(world)]
+            flat = [i for c in chunks for i in c]
+            assert flat == list(range(n))
+            assert max(len(c) for c in chunks) - min(len(c) for c in chunks) <= 1
+    with pytest.raises(ValueError):
+        shard_frames(10, 2, 2)
+
+
+def _gather_worker(rank, world, n_frames, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from semantic_depth_b200.stream import gather_results, pack_answers, shard_frames
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = shard_frames(n_frames, rank, world)
+    rw = np.array([7.0 + 0.01 * i for i in mine])
+    f2f = np.array([7.5 - 0.01 * i for i in mine])
+    status = np.array([i % 3 for i in mine])
+    allr = gather_results(pack_answers(rw, f2f, status), n_frames)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), allr.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [7, 12])
+def test_frame_parallel_gather_world2_gloo(tmp_path, n_frames):
+    """The N>1 host path: frames sharded over 2 ranks, answers all-gathered into frame order (gloo, CPU)."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() % 2000) + n_frames
+    mp.spawn(_gather_worker, args=(2, n_frames, port, str(tmp_path)), nprocs=2, join=True)
+    expect = np.stack([[7.0 + 0.01 * i for i in range(n_frames)], [7.5 - 0.01 * i for i in range(n_frames)],
+                       [float(i % 3) for i in range(n_frames)]], axis=1)
+    for r in range(2):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npy"))
+        np.testing.assert_array_equal(got, expect)
+
+
+def test_bench_alg_bytes_matches_survey_formula():
+    sys.path.insert(0, ROOT)
+    import bench
+    counts = {"road_gather": 606837, "fence_gather": 691785, "road_z": 452841, "road_mad_y": 450831, "road_mad_x": 450831,
+              "road_plane": 450831, "road_sor": 391988, "road_ror": 390743, "fence_mad_y": 691424, "fence_abs_z": 666758,
+              "left_split": 326266, "right_split": 340492, "left_mad_x": 325826, "left_plane": 325826,
+              "right_mad_x": 232772, "right_plane": 232772}
+    b = bench.b_alg_bytes(counts, 1024 * 2048)
+    assert abs(b / 1e6 - 203.9) < 0.5      # 203.9 MB for the seed-0 frame

@@ -1,0 +1,112 @@
+"""CPU suite: the oracle against the committed golden vectors.
+
+The vectors under tests/golden were produced by tests/golden/make_golden.py in the build container, where the
+reference's own semantic_depth_lib/pcl.py (imported unmodified), its DepthFrame.post_processing /
+compute_3D_points (lifted with ast, real cv2) and the oracle were asserted bit-equal.  Here the oracle alone is
+re-checked against those vectors (the reference does not exist on the GPU box)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import frame_ref, pcl_ref
+from semantic_depth_b200 import scene
+from semantic_depth_b200.params import FusionParams, Intrinsics
+
+CASES = ["rand1", "rand2", "rand7", "rand8", "rand9", "rand127", "rand128", "rand129", "rand1000", "rand4097",
+         "dups", "mad_zero", "with_inf", "fp64"]
+
+
+@pytest.fixture(scope="module")
+def vec(golden_dir):
+    return np.load(os.path.join(golden_dir, "pcl_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_pcl_keep_indices(vec, name):
+    pts = vec[f"{name}/pts"]
+    with np.errstate(all="ignore"):
+        assert np.array_equal(pcl_ref.keep_remove_from_to(pts, 2, 7.0), vec[f"{name}/keep_z7"])
+        assert np.array_equal(pcl_ref.keep_threshold_complete(pts, 2, 35.0), vec[f"{name}/keep_absz35"])
+        for axis, thr in ((1, 15.0), (0, 2.0), (1, 5.0), (0, 5.0), (0, 1.0), (2, 3.0)):
+            assert np.array_equal(pcl_ref.keep_mad(pts, axis, thr), vec[f"{name}/keep_mad_{axis}_{thr}"])
+            _, m = pcl_ref.mad(pts[:, axis])
+            a, b = np.asarray(m), vec[f"{name}/mad_{axis}"]
+            assert (a == b) or (np.isnan(a) and np.isnan(b))
+        kl, kr, mean = pcl_ref.keep_extract_pcls(pts)
+        assert np.array_equal(kl, vec[f"{name}/keep_left"]) and np.array_equal(kr, vec[f"{name}/keep_right"])
+        for depth in (9.98, 30.0):
+            assert np.array_equal(pcl_ref.keep_slab(pts, depth), vec[f"{name}/keep_slab_{depth}"])
+        if f"{name}/coef_plane_1" in vec:
+            for axis, thr in ((1, 5.0), (0, 1.0), (2, 2.0), (1, 0.3)):
+                keep, C = pcl_ref.keep_plane(pts, axis, thr)
+                np.testing.assert_allclose(C, vec[f"{name}/coef_plane_{axis}"], rtol=1e-9, atol=1e-11)
+                res = np.abs(pcl_ref.plane_residual(pts, axis, vec[f"{name}/coef_plane_{axis}"]))
+                if np.min(np.abs(res - thr)) > 1e-8:
+                    assert np.array_equal(keep, vec[f"{name}/keep_plane_{axis}_{thr}"])
+
+
+def test_pcl_surface_shapes(vec):
+    pts = vec["rand1000/pts"]
+    cols = (np.arange(pts.shape[0] * 3).reshape(-1, 3) % 251).astype(np.uint8)
+    out = pcl_ref.remove_noise_by_fitting_plane(pts, cols, axis=1, threshold=5.0, plane_color=[200, 200, 200])
+    assert len(out) == 5 and list(out[4]) == ["Cx", "Cy", "Cz", "C"] and out[4]["Cy"] == -1.0
+    assert len(pcl_ref.extract_pcls(pts, cols)) == 4
+    assert pcl_ref.get_end_points_of_road(pts[:0], 9.98) == (None, None)
+    got = pcl_ref.planes_intersection_at_certain_depth({"Cx": 0.01, "Cy": -1.0, "Cz": 0.002, "C": -1.5},
+                                                       {"Cx": -1.0, "Cy": 0.03, "Cz": 0.001, "C": -4.0}, 10.0)
+    assert np.array_equal(got, vec["intersect/expected"])
+    pa, pb = np.float64([[1.0, 2.0, -10.0]]), np.float64([[-3.0, 2.5, -10.0]])
+    line, _ = pcl_ref.create_3Dline_from_3Dpoints(pa, pb, [250, 0, 0])
+    assert np.array_equal(line, vec["line/expected"])
+    with pytest.raises(ValueError):
+        pcl_ref.remove_from_to(pts[:0], cols[:0], 2, 0.0, 7.0)
+
+
+def test_pixel_vectors(golden_dir):
+    g = np.load(os.path.join(golden_dir, "pixel_vectors.npz"))
+    for tag in ("city", "munich", "synth"):
+        blend = frame_ref.post_process_disparity(g[f"{tag}/disp"])
+        assert blend.dtype == np.float32 and np.array_equal(blend.view(np.uint32), g[f"{tag}/blend"].view(np.uint32))
+        with np.errstate(all="ignore"):
+            pts = frame_ref.reproject_to_3d(blend * np.float32(g[f"{tag}/mult"]), g[f"{tag}/q32"])
+        ref = g[f"{tag}/points"]
+        assert np.all((pts == ref) | (np.isnan(pts) & np.isnan(ref)))
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "frame_*.npz"))))
+def test_frame_fixture(path):
+    g = np.load(path)
+    h, w, seed = int(g["h"]), int(g["w"]), int(g["seed"])
+    if h * w > 256 * 512:
+        pytest.skip("large fixture is exercised by the GPU suite (keeps the CPU suite short)")
+    logits, disp, intr = scene.make_frame(h, w, seed)
+    o = frame_ref.fuse_frame(logits, disp, intr.as_q32(), intr.disparity_mult, FusionParams())
+    for name, c in o["counts"].items():
+        assert c == int(g[f"count/{name}"]), name
+        if f"src/{name}" in g:
+            assert np.array_equal(o["src"][name], g[f"src/{name}"]), name
+    assert o["status"] == int(g["status"])
+    rw = float(g["rw"])
+    assert (o["rw"] is None and np.isnan(rw)) or o["rw"] == rw
+    assert o["f2f"] == float(g["f2f"])
+
+
+def test_ransac_oracle_reduces_to_least_squares_shape():
+    rng = np.random.default_rng(0)
+    pts = (rng.standard_normal((2000, 3)) * np.array([3.0, 0.05, 10.0]) + np.array([0, -1.5, -30.0])).astype(np.float32)
+    trip = rng.integers(0, 2000, (64, 3))
+    trip[3] = [5, 5, 9]
+    counts = frame_ref.ransac_inlier_counts(pts, 1, 0.1, trip)
+    assert counts.shape == (64,) and counts[3] == 0 and counts.max() > 1000
+    keep, C, best, _ = frame_ref.keep_plane_ransac(pts, 1, 0.1, trip)
+    assert best == int(np.argmax(counts)) and abs(C[2] + 1.5) < 0.05 and keep.size > 1000
+
+
+def test_sor_ror_oracle_small():
+    pts = scene.make_road_cloud(3000, seed=1)
+    keep, avg, (thr, mu, sd) = frame_ref.keep_statistical_outlier_removal(pts, 10, 0.5)
+    assert avg.shape == (3000,) and np.all(avg > 0) and thr == mu + 0.5 * sd and 0 < keep.size < 3000
+    cnt = frame_ref.radius_counts(pts, 0.5)
+    assert cnt.min() >= 1 and np.array_equal(frame_ref.keep_radius_outlier_removal(pts, 80, 0.5), np.flatnonzero(cnt > 80))

@@ -123,8 +123,7 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->cell_count = c.take<int32_t>(F * ((size_t)ws->cell_cap + 8));
     ws->cell_start = c.take<int32_t>(F * ((size_t)ws->cell_cap + 8));
     ws->cell_of = c.take<int32_t>(F * cap);
-    ws->sx = c.take<float>(F * cap); ws->sy = c.take<float>(F * cap); ws->sz = c.take<float>(F * cap);
-    ws->sorig = c.take<int32_t>(F * cap);
+    ws->sp = c.take<float4>(F * cap * kLevels);
     ws->avg = c.take<double>(F * cap); ws->savg = c.take<double>(F * cap);
     ws->cnt = c.take<int32_t>(F * cap);
     ws->knn_part = c.take<double>((size_t)F * kKnnMaxBlocks * 3);
@@ -150,7 +149,7 @@ void set_dims(SdWorkspace* ws, int max_frames, int height, int width, int max_hy
     ws->cap = round_up(height * width, kCompactTile);
     ws->max_tiles = ws->cap / kCompactTile;
     ws->pix_tiles = (height * width + 1023) / 1024;
-    ws->cell_cap = ws->cap;
+    ws->cell_cap = 2 * ws->cap + 4096;          // all grid levels together; the cell edge grows until they fit
     ws->grid_tiles = (ws->cell_cap + kScanTile - 1) / kScanTile + 1;
 }
 
@@ -217,7 +216,7 @@ void fill_knn(KnnJob& j, const float* x, const float* y, const float* z, const i
     j.x = x; j.y = y; j.z = z; j.n = n;
     j.gs = ws->gs + f;
     j.cell_count = ws->cell_count + oc; j.cell_start = ws->cell_start + oc; j.cell_of = ws->cell_of + o;
-    j.sx = ws->sx + o; j.sy = ws->sy + o; j.sz = ws->sz + o; j.sorig = ws->sorig + o;
+    j.sp = ws->sp + o * kLevels;
     j.avg = ws->avg + o; j.savg = ws->savg + o; j.cnt = ws->cnt + o;
     j.scan_status = ws->gstatus + (size_t)f * ws->grid_tiles; j.scan_ctl = ws->gctl + f;
     j.cell_cap = ws->cell_cap;
@@ -302,8 +301,8 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     const char* sm = getenv("SD_SOR_MODE");
     pv->organized = (sm && strcmp(sm, "organized") == 0);     // default: world-space grid search
     const char* cs = getenv("SD_KNN_CELL_SCALE");
-    pv->cell_scale = cs ? atof(cs) : 1.0;
-    if (!(pv->cell_scale > 0.0)) pv->cell_scale = 1.0;
+    pv->cell_scale = cs ? atof(cs) : 0.6;
+    if (!(pv->cell_scale > 0.0)) pv->cell_scale = 0.6;
     ws->fused_ready = false;
     *out = ws;
     return SD_OK;
@@ -748,6 +747,7 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     } else {
         if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
         if (P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
+        if (P.use_sor && P.use_ror) SD_RUN(sd_launch_sor_stats(T.k_road, B, cap, st));
         if (P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
     }
     SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
@@ -791,6 +791,7 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     } else {
         if (P->use_sor || P->use_ror) n += 4;    // grid: bbox, count, scan, scatter
         if (P->use_sor) n += 1;
+        if (P->use_sor && P->use_ror) n += 1;    // statistical filter applied to the cell-sorted copy
         if (P->use_ror) n += 1;
     }
     n += 1 + 1;                                  // final road compaction, slab
@@ -838,7 +839,8 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
 extern "C" int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8) {
     if (!ws || !h_out8 || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_debug_counters: bad argument");
     SD_CUDA_TRY(cudaDeviceSynchronize());
-    SD_CUDA_TRY(cudaMemcpy(h_out8, ws->ost[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+    if (priv(ws)->organized) SD_CUDA_TRY(cudaMemcpy(h_out8, ws->ost[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+    else SD_CUDA_TRY(cudaMemcpy(h_out8, ws->gs[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
     return SD_OK;
 }
 

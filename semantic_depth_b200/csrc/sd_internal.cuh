@@ -15,6 +15,7 @@ constexpr int kScanTile = 4096;                                 // cell-count sc
 constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job
 constexpr int kPlaneSums = 9;
 constexpr int kMaxKnnK = 64;
+constexpr int kLevels = 3;                                      // grid resolutions of the neighbour search (cell edge x4 per level)
 
 // ---- device-side per-frame scalars --------------------------------------------------------------
 struct FrameState {
@@ -112,9 +113,10 @@ struct SlabJob {
 struct GridState {
     uint32_t bbox[6];           // ordered keys: min x,y,z then max x,y,z  (reset by the last bbox block)
     uint32_t ticket;
-    int32_t ncells;
+    int32_t ncells;             // over all levels
     int32_t a0, a1, a2;         // a0 = fast grid axis, a1 = slow grid axis, a2 = collapsed axis
-    int32_t d0, d1;             // cells along a0 / a1
+    int32_t d0, d1;             // level-0 cells along a0 / a1
+    int32_t ld0[kLevels], ld1[kLevels], loff[kLevels];   // per level: cells along a0 / a1, offset into the cell arrays
     int32_t n;                  // snapshot of the cloud size
     double o0, o1;              // grid origin along a0 / a1
     double cell, inv_cell;
@@ -122,14 +124,16 @@ struct GridState {
     unsigned long long acc[3][2];  // exact 128-bit fixed-point sums of avg, avg^2 (lo, hi) and the count of avg > 0
     int32_t work;                  // dynamic work counter of the search kernels (next unclaimed sorted index)
     int32_t pad_;
+    unsigned long long dbg[8];     // developer counters (cumulative): 0 k-NN queries, 1 slow-path queries, 2 list overflows,
+                                   // 3 list underflows, 4 sum of list lengths, 5 phase-1 candidates, 6 phase-2 candidates, 7 phase-2 rows
 };
 struct KnnJob {
     const float* x; const float* y; const float* z; const int32_t* n;
     GridState* gs;
-    int32_t* cell_count;        // [cell_cap + 1], all zero between launches
-    int32_t* cell_start;        // [cell_cap + 1]
-    int32_t* cell_of;           // [cap] cell of each point (input order)
-    float* sx; float* sy; float* sz; int32_t* sorig;   // cell-sorted copies
+    int32_t* cell_count;        // [cell_cap + 1] all levels concatenated, all zero between launches
+    int32_t* cell_start;        // [cell_cap + 1] absolute positions into the sorted copies
+    int32_t* cell_of;           // [cap] level-0 cell of each point (input order)
+    float4* sp;                 // [kLevels * cap] cell-sorted copies (x, y, z, bits(original index)), level L at [L*n, (L+1)*n)
     double* avg;                // [cap] mean kNN distance, by ORIGINAL index
     double* savg;               // [cap] same, by sorted index
     int32_t* cnt;               // [cap] radius counts, by original index
@@ -263,7 +267,7 @@ struct SdWorkspace {
     // grid / knn per frame
     sd::GridState* gs;                   // [F]
     int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
-    float* sx; float* sy; float* sz; int32_t* sorig;
+    float4* sp;
     double* avg; double* savg; int32_t* cnt; double* knn_part;
     float4* dense; sd::OrgState* ost; int32_t* queue_knn; int32_t* queue_ror;   // organized search (fused path)
     unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
@@ -287,7 +291,7 @@ int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, cudaStream_t st);
 int sd_launch_slab(const sd::SlabJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
-int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, cudaStream_t st);
+int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_org_fill(float4* dense, size_t count, cudaStream_t st);
 int sd_launch_org_knn(const sd::OrgJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);

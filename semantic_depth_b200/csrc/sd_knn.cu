@@ -1,18 +1,24 @@
-// Uniform-grid neighbour search: the two Open3D filters of the road chain
+// Multi-resolution uniform-grid neighbour search: the two Open3D filters of the road chain
 // (semantic_depth.py:227-245; Open3D <= 0.7 RemoveStatisticalOutliers / RemoveRadiusOutliers).
 //
 // The reference runs a FLANN KD-tree on the host.  Here the cloud is binned into a 2-D uniform grid
 // over its two widest axes (road clouds are 2.5-D slabs; the third axis is collapsed, which keeps
-// every bound below a valid lower bound of the 3-D distance), points are counting-sorted by cell
-// (integer atomics only: cell order inside a cell is arbitrary but the k smallest distances and the
-// radius counts do not depend on it), and each point searches rings / rows of cells outwards until
-// the current k-th distance (or the radius) proves that no unvisited cell can matter.  Distances are
-// fp64 `(dx*dx + dy*dy) + dz*dz` without FMA, sqrt is IEEE, the k distances are summed in ascending
-// order from 0.0 -- the arithmetic of FLANN's L2 functor + std::accumulate -- so the per-point
-// mean distance is bit-identical to the CPU oracle.  An fp32 pre-test with a proven error margin
-// rejects most candidates before the fp64 evaluation.
+// every bound below a valid lower bound of the 3-D distance).  A road cloud seen through a pinhole
+// camera has a point density that falls with the cube of the depth (1500x between 7 m and 80 m), so
+// one cell size cannot fit: the grid is kept at kLevels resolutions (cell edge x4 per level, cells of
+// level L+1 are exact unions of 4x4 cells of level L), each with its own counting-sorted copy of the
+// cloud (integer atomics only: the order inside a cell is arbitrary, but the k smallest distances and
+// the radius counts do not depend on it).  Every query works at the finest level whose 3x3 cells
+// around it hold enough points, so that its search disc always spans a handful of grid rows, each of
+// which is ONE contiguous run of the level's sorted copy.
 //
-// Not HBM-bound: the sorted cloud (<= 8 MB) lives in L2; the cost is L2 latency + fp64 ALU.
+// Distances that reach a result are fp64 `(dx*dx + dy*dy) + dz*dz` without FMA, sqrt is IEEE, the k
+// distances are summed in ascending order from 0.0 -- the arithmetic of FLANN's L2 functor +
+// std::accumulate -- so the per-point mean distance is bit-identical to the CPU oracle.  fp32 keys
+// are only ever used to discard candidates with a proven error margin.
+//
+// Not HBM-bound: the sorted copies (<= 3 x 5.4 MB per frame) live in L2/L1; the cost is instruction
+// issue + L1/L2 latency.
 #include "sd_internal.cuh"
 
 namespace sd {
@@ -75,11 +81,19 @@ grid_bbox_kernel(const KnnJob* __restrict__ jobs) {
     long long d0, d1;
     for (int it = 0; it < 64; ++it) {
         d0 = (long long)floor(ext[a0] / cell) + 1; d1 = (long long)floor(ext[a1] / cell) + 1;
-        if (d0 * d1 <= (long long)J.cell_cap && d0 < (1 << 24) && d1 < (1 << 24)) break;
+        // all levels together hold < 1.07x the level-0 cells (+ one partial cell per row / column and level)
+        if (d0 * d1 + (d0 * d1) / 8 + d0 + d1 + 64 <= (long long)J.cell_cap && d0 < (1 << 24) && d1 < (1 << 24)) break;
         cell *= 1.25;
     }
     gs->a0 = a0; gs->a1 = a1; gs->a2 = a2;
-    gs->d0 = (int)d0; gs->d1 = (int)d1; gs->ncells = (int)(d0 * d1);
+    gs->d0 = (int)d0; gs->d1 = (int)d1;
+    int off = 0;
+    for (int L = 0; L < kLevels; ++L) {
+        const int e0 = (((int)d0 - 1) >> (2 * L)) + 1, e1 = (((int)d1 - 1) >> (2 * L)) + 1;
+        gs->ld0[L] = e0; gs->ld1[L] = e1; gs->loff[L] = off;
+        off += e0 * e1;
+    }
+    gs->ncells = off;
     gs->o0 = lo[a0]; gs->o1 = lo[a1];
     gs->cell = cell; gs->inv_cell = 1.0 / cell; gs->ext2 = ext[a2];
     gs->n = n;
@@ -87,8 +101,23 @@ grid_bbox_kernel(const KnnJob* __restrict__ jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// 2. counting sort by cell: count -> exclusive scan (look-back) -> scatter
+// 2. counting sort by cell at every level: count -> exclusive scan (look-back) -> scatter.
+//    Levels are concatenated: cell arrays [level 0 | level 1 | level 2], sorted copies likewise, so one
+//    scan yields absolute positions (level L occupies [L*n, (L+1)*n)).  Coarse cells receive thousands
+//    of points each: their atomics are aggregated per warp with match_any.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int aggregated_add(int32_t* addr, int sign) {
+    // the lanes that target `addr` elect a leader; returns what a private atomicAdd(addr, sign) would have
+    // returned to this lane had the lanes gone one after the other
+    const unsigned mask = __match_any_sync(__activemask(), (unsigned long long)addr);
+    const int leader = __ffs(mask) - 1, lane = lane_id();
+    const int rank = __popc(mask & ((1u << lane) - 1u)), total = __popc(mask);
+    int old = 0;
+    if (lane == leader) old = atomicAdd(addr, sign * total);
+    old = __shfl_sync(mask, old, leader);
+    return old + sign * rank;
+}
+
 __global__ void __launch_bounds__(kGridThreads)
 grid_count_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
@@ -97,9 +126,11 @@ grid_count_kernel(const KnnJob* __restrict__ jobs) {
         const float x = __ldg(J.x + i), y = __ldg(J.y + i), z = __ldg(J.z + i);
         const int c0 = cell_coord((double)pick_axis(g.a0, x, y, z), g.o0, g.inv_cell, g.d0);
         const int c1 = cell_coord((double)pick_axis(g.a1, x, y, z), g.o1, g.inv_cell, g.d1);
-        const int c = c1 * g.d0 + c0;
-        J.cell_of[i] = c;
-        atomicAdd(&J.cell_count[c], 1);
+        J.cell_of[i] = c1 * g.d0 + c0;
+        atomicAdd(&J.cell_count[c1 * g.d0 + c0], 1);
+#pragma unroll
+        for (int L = 1; L < kLevels; ++L)
+            aggregated_add(&J.cell_count[g.loff[L] + (c1 >> (2 * L)) * g.ld0[L] + (c0 >> (2 * L))], 1);
     }
 }
 
@@ -143,13 +174,22 @@ grid_scan_kernel(const KnnJob* __restrict__ jobs) {
 __global__ void __launch_bounds__(kGridThreads)
 grid_scatter_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
-    const int n = J.gs->n;
-    for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
+    const GridState g = *J.gs;
+    for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < g.n; i += gridDim.x * kGridThreads) {
         const int c = J.cell_of[i];
-        const int k = atomicSub(&J.cell_count[c], 1) - 1;     // leaves cell_count all-zero again
-        const int pos = J.cell_start[c] + k;
-        J.sx[pos] = __ldg(J.x + i); J.sy[pos] = __ldg(J.y + i); J.sz[pos] = __ldg(J.z + i);
-        J.sorig[pos] = i;
+        const int c1 = c / g.d0, c0 = c - c1 * g.d0;
+        const float x = __ldg(J.x + i), y = __ldg(J.y + i), z = __ldg(J.z + i);
+        const float4 pt = make_float4(x, y, z, __int_as_float(i));
+        {   // atomicSub leaves cell_count all-zero again
+            const int pos = J.cell_start[c] + atomicSub(&J.cell_count[c], 1) - 1;
+            J.sp[pos] = pt;
+        }
+#pragma unroll
+        for (int L = 1; L < kLevels; ++L) {
+            const int cl = g.loff[L] + (c1 >> (2 * L)) * g.ld0[L] + (c0 >> (2 * L));
+            const int pos = J.cell_start[cl] + aggregated_add(&J.cell_count[cl], -1) - 1;
+            J.sp[pos] = pt;
+        }
     }
 }
 
@@ -157,15 +197,34 @@ grid_scatter_kernel(const KnnJob* __restrict__ jobs) {
 // 3. exact kNN mean distance (Open3D RemoveStatisticalOutliers, per point)
 // ---------------------------------------------------------------------------------------------
 struct GridRt {
-    int a0, a1, d0, d1, n;
+    int a0, a1, n;
+    int d0[kLevels], d1[kLevels], off[kLevels];
     double o0, o1, cell, inv_cell, slack;
 };
 __device__ __forceinline__ GridRt load_grid(const GridState* gs) {
     GridRt g;
-    g.a0 = gs->a0; g.a1 = gs->a1; g.d0 = gs->d0; g.d1 = gs->d1; g.n = gs->n;
+    g.a0 = gs->a0; g.a1 = gs->a1; g.n = gs->n;
+#pragma unroll
+    for (int L = 0; L < kLevels; ++L) { g.d0[L] = gs->ld0[L]; g.d1[L] = gs->ld1[L]; g.off[L] = gs->loff[L]; }
     g.o0 = gs->o0; g.o1 = gs->o1; g.cell = gs->cell; g.inv_cell = gs->inv_cell;
     g.slack = gs->cell * kSlackRel;
     return g;
+}
+// one level of the grid as the search loops see it
+struct LevelRt {
+    int d0, d1; const int32_t* cs;       // cell_start of this level (absolute positions into the sorted copies)
+    double cell, inv_cell; int shift;
+};
+__device__ __forceinline__ LevelRt level_of(const KnnJob& J, const GridRt& g, int L) {
+    LevelRt v;
+    v.d0 = g.d0[0]; v.d1 = g.d1[0]; int off = 0;
+#pragma unroll
+    for (int l = 1; l < kLevels; ++l) if (l == L) { v.d0 = g.d0[l]; v.d1 = g.d1[l]; off = g.off[l]; }
+    v.cs = J.cell_start + off;
+    v.shift = 2 * L;
+    const double s = (double)(1 << (2 * L));
+    v.cell = g.cell * s; v.inv_cell = g.inv_cell / s;      // exact power-of-two scaling
+    return v;
 }
 
 template <int KCAP>
@@ -194,12 +253,12 @@ struct Best {
     }
 };
 
-// ---- slow exact path: fp64 keys, ring by ring (used when the fp32-keyed search cannot certify its set)
+// ---- slow exact path: fp64 keys, ring by ring on the finest level (only reached on massive ties)
 template <int KCAP>
 __device__ __forceinline__ void scan_range_exact(const KnnJob& J, int s, int e, float qx, float qy, float qz, Best<KCAP>& best) {
     for (int j = s; j < e; ++j) {
-        const float px = __ldg(J.sx + j), py = __ldg(J.sy + j), pz = __ldg(J.sz + j);
-        const double dx = (double)px - (double)qx, dy = (double)py - (double)qy, dz = (double)pz - (double)qz;
+        const float4 p = __ldg(J.sp + j);
+        const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
         const double d2 = (dx * dx + dy * dy) + dz * dz;
         if (d2 < best.d[0]) best.insert(d2);
     }
@@ -209,23 +268,24 @@ template <int KCAP>
 __device__ __noinline__ double knn_exact_sum(const KnnJob& J, const GridRt& g, float qx, float qy, float qz, double q0, double q1,
                                               int c0, int c1, int keff) {
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    const int D0 = g.d0[0], D1 = g.d1[0];
     Best<KCAP> best; best.init(keff);
     for (int r = 0;; ++r) {
         const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
-        const int cl0 = max(lo0, 0), ch0 = min(hi0, g.d0 - 1);
-        for (int row = max(lo1, 0); row <= min(hi1, g.d1 - 1); ++row) {
-            const int rb = row * g.d0;
+        const int cl0 = max(lo0, 0), ch0 = min(hi0, D0 - 1);
+        for (int row = max(lo1, 0); row <= min(hi1, D1 - 1); ++row) {
+            const int rb = row * D0;
             if (row == lo1 || row == hi1) {
                 scan_range_exact<KCAP>(J, J.cell_start[rb + cl0], J.cell_start[rb + ch0 + 1], qx, qy, qz, best);
             } else {
                 if (lo0 >= 0) scan_range_exact<KCAP>(J, J.cell_start[rb + lo0], J.cell_start[rb + lo0 + 1], qx, qy, qz, best);
-                if (hi0 < g.d0) scan_range_exact<KCAP>(J, J.cell_start[rb + hi0], J.cell_start[rb + hi0 + 1], qx, qy, qz, best);
+                if (hi0 < D0) scan_range_exact<KCAP>(J, J.cell_start[rb + hi0], J.cell_start[rb + hi0 + 1], qx, qy, qz, best);
             }
         }
         const double e_lo0 = (lo0 <= 0) ? inf : q0 - (g.o0 + (double)lo0 * g.cell);
-        const double e_hi0 = (hi0 >= g.d0 - 1) ? inf : (g.o0 + (double)(hi0 + 1) * g.cell) - q0;
+        const double e_hi0 = (hi0 >= D0 - 1) ? inf : (g.o0 + (double)(hi0 + 1) * g.cell) - q0;
         const double e_lo1 = (lo1 <= 0) ? inf : q1 - (g.o1 + (double)lo1 * g.cell);
-        const double e_hi1 = (hi1 >= g.d1 - 1) ? inf : (g.o1 + (double)(hi1 + 1) * g.cell) - q1;
+        const double e_hi1 = (hi1 >= D1 - 1) ? inf : (g.o1 + (double)(hi1 + 1) * g.cell) - q1;
         double lb = fmin(fmin(e_lo0, e_hi0), fmin(e_lo1, e_hi1));
         if (lb == inf) break;
         lb = lb - g.slack;
@@ -235,16 +295,39 @@ __device__ __noinline__ double knn_exact_sum(const KnnJob& J, const GridRt& g, f
 }
 
 // ---- fast path -------------------------------------------------------------------------------------
-// Phase 1: every candidate of the search square goes through a branch-free sorted-insertion network on
-//          fp32 keys (2 FMNMX per slot, all lanes active, no divergence): the k+1 smallest keys survive.
-// Phase 2: the square is rescanned and the candidates whose key is within the fp32 error band of the
-//          k-th key are collected (indices, shared memory, <= kListCap per query).  Every true member of
-//          the exact k-set is in that list (see DESIGN.md "k-NN exactness").
-// Phase 3: fp64 distances of the collected candidates, exact branch-free selection of the k smallest,
-//          sqrt and ascending sum -- the arithmetic of the oracle.
-// A query whose list overflows (massive ties) is redone by the fp64-keyed slow path.
-constexpr int kListCap = 16;
+// One query per lane; every loop a lane runs is either short and uniform or *flattened* (one trip per
+// candidate, whatever grid row it comes from), so lanes of a warp stay busy until the lane with the most
+// candidates is done.
+// Level:   the finest grid level whose 3x3 cells around the query hold at least 2k points.
+// Phase 1 (bound): up to 2k+14 of those points -- a window of the level's sorted copy in the query's row and
+//          one in each adjacent row -- go through a branch-free sorted-insertion network on fp32 keys.  The
+//          k-th smallest key U of ANY k-subset of the cloud is an upper bound of the true k-th squared
+//          distance.  (Fewer than 2k points even at the coarsest level: rings of coarse cells grow.)
+// Phase 2 (collect): the disc of radius sqrt(U) around the query is swept (one contiguous run of the sorted
+//          copy per grid row; run bounds are staged in shared memory so the sweep is a single flattened loop)
+//          with a compare + append: candidates whose key is within the fp32 error band of U go to a per-query
+//          list in shared memory.  Every true member of the exact k-set is in that list (DESIGN.md "k-NN
+//          exactness").  A list overflow tightens U from the listed keys and sweeps again.
+// Phase 3 (select): the listed keys, truncated by 7 bits and tagged with their list slot, go through an
+//          integer network (2 VIMNMX per slot); the k winners are re-evaluated in fp64 -- (dx*dx+dy*dy)+dz*dz,
+//          IEEE sqrt, ascending sum from 0.0: the arithmetic of the oracle.  If the k-th and (k+1)-th
+//          truncated keys are closer than two truncation cells (3e-5 relative, far above the fp32 error) or the
+//          fp64 values are not ascending, the whole list is re-selected in fp64.
+// A query whose list still overflows after three tightenings (massive ties) is redone by the fp64 slow path.
 constexpr float kKeyErr = 1.5e-6f;     // relative error bound of the fp32 squared distance
+constexpr int kSlotBits = 7;
+constexpr int kMaxRows = 8;            // row runs staged per query; wider discs use the nested sweep
+
+template <int K> struct KnnCfg {
+    static constexpr int own_win = K + 4;                                 // phase-1 window in the query's own row
+    static constexpr int side_win = K / 2 + 5;                            // ... in each adjacent row
+    static constexpr int min_fed = K + 2;                                 // fewer points than this in the 3x3 cells: coarser level
+    static constexpr int feed_all = 2 * K + 14;                           // up to this many points in the 3x3 cells: all of them are fed
+    static constexpr int feed_cap = 4 * K + 24;                           // ... ring mode
+    static constexpr int list_raw = 3 * K + 10;
+    static constexpr int list_cap = list_raw > 126 ? 126 : list_raw;      // phase-2 list entries per query (smem, 7-bit slots)
+    static constexpr size_t smem_bytes = ((size_t)list_cap * sizeof(int) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;
+};
 
 template <int KS>
 struct FNet {
@@ -265,107 +348,336 @@ struct FNet {
     }
 };
 
-__device__ __forceinline__ float key_f32(const KnnJob& J, int j, float qx, float qy, float qz) {
-    const float fx = __ldg(J.sx + j) - qx, fy = __ldg(J.sy + j) - qy, fz = __ldg(J.sz + j) - qz;
-    return (fx * fx + fy * fy) + fz * fz;               // identical expression in phases 1 and 2
-}
+template <int KS>
+struct UNetK {
+    uint32_t d[KS];                      // ascending
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int p = 0; p < KS; ++p) d[p] = 0xffffffffu;
+    }
+    __device__ __forceinline__ void feed(uint32_t v) {
+#pragma unroll
+        for (int p = 0; p < KS; ++p) { const uint32_t lo = min(d[p], v); v = max(d[p], v); d[p] = lo; }
+    }
+    __device__ __forceinline__ uint32_t get(int idx) const {
+        uint32_t r = d[0];
+#pragma unroll
+        for (int p = 1; p < KS; ++p) r = (p == idx) ? d[p] : r;
+        return r;
+    }
+};
 
-// visit the cells that square(r) adds to square(rold) (rold < 0: everything), row by row
+__device__ __forceinline__ float key_of(const float4& p, float qx, float qy, float qz) {
+    const float fx = p.x - qx, fy = p.y - qy, fz = p.z - qz;
+    return (fx * fx + fy * fy) + fz * fz;               // identical expression in every phase
+}
+__device__ __forceinline__ float key_f32(const KnnJob& J, int j, float qx, float qy, float qz) {
+    return key_of(__ldg(J.sp + j), qx, qy, qz);
+}
+__device__ __forceinline__ double dist2_of(const float4& p, float qx, float qy, float qz) {
+    const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;
+    return (dx * dx + dy * dy) + dz * dz;
+}
+__device__ __forceinline__ double dist2_f64(const KnnJob& J, int j, float qx, float qy, float qz) {
+    return dist2_of(__ldg(J.sp + j), qx, qy, qz);
+}
+constexpr int kBatch = 4;              // candidates whose loads are issued together (the loops are latency-bound)
+
+// visit the cells that square(r) adds to square(rold) (rold < 0: everything) at one level, row by row
 template <typename F>
-__device__ __forceinline__ void for_new_segments(const KnnJob& J, const GridRt& g, int c0, int c1, int r, int rold, F&& f) {
+__device__ __forceinline__ void for_new_segments(const LevelRt& lv, int c0, int c1, int r, int rold, F&& f) {
     const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
-    const int cl0 = max(lo0, 0), ch0 = min(hi0, g.d0 - 1);
-    for (int row = max(lo1, 0); row <= min(hi1, g.d1 - 1); ++row) {
-        const int rb = row * g.d0;
+    const int cl0 = max(lo0, 0), ch0 = min(hi0, lv.d0 - 1);
+    for (int row = max(lo1, 0); row <= min(hi1, lv.d1 - 1); ++row) {
+        const int rb = row * lv.d0;
         if (rold < 0 || row < c1 - rold || row > c1 + rold) {
-            f(J.cell_start[rb + cl0], J.cell_start[rb + ch0 + 1]);
+            f(lv.cs[rb + cl0], lv.cs[rb + ch0 + 1]);
         } else {
             const int le = min(c0 - rold - 1, ch0), rs = max(c0 + rold + 1, cl0);
-            if (le >= cl0) f(J.cell_start[rb + cl0], J.cell_start[rb + le + 1]);
-            if (rs <= ch0) f(J.cell_start[rb + rs], J.cell_start[rb + ch0 + 1]);
+            if (le >= cl0) f(lv.cs[rb + cl0], lv.cs[rb + le + 1]);
+            if (rs <= ch0) f(lv.cs[rb + rs], lv.cs[rb + ch0 + 1]);
         }
     }
 }
 
+// runs of the 3x3 cells around level-0 cell (c0, c1) at level L: own row, row + 1, row - 1
+__device__ __forceinline__ int block3_runs(const KnnJob& J, const GridRt& g, int L, int c0, int c1, int* s3, int* e3) {
+    const int d0 = g.d0[L], d1 = g.d1[L];
+    const int32_t* cs = J.cell_start + g.off[L];
+    const int k0 = c0 >> (2 * L), k1 = c1 >> (2 * L);
+    const int cl = max(k0 - 1, 0), ch = min(k0 + 1, d0 - 1);
+    int total = 0;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int row = k1 + (t == 0 ? 0 : (t == 1 ? 1 : -1));
+        int s = 0, e = 0;
+        if (row >= 0 && row < d1) { s = __ldg(cs + row * d0 + cl); e = __ldg(cs + row * d0 + ch + 1); }
+        s3[t] = s; e3[t] = e; total += e - s;
+    }
+    return total;
+}
+
+// run [s, e) of the level's sorted copy that covers the disc (q, rad) inside grid row `row` (empty when the row misses it)
+__device__ __forceinline__ void row_run(const GridRt& g, const LevelRt& lv, double q0, double q1, double rad, int k1, int row,
+                                        int& s, int& e) {
+    double gap = 0.0;                                // distance from q to the row's slab along a1
+    if (row > k1) gap = (g.o1 + (double)row * lv.cell) - q1;
+    else if (row < k1) gap = q1 - (g.o1 + (double)(row + 1) * lv.cell);
+    gap -= g.slack;
+    s = 0; e = 0;
+    if (gap > rad) return;
+    if (gap < 0.0) gap = 0.0;
+    const double half = (double)sqrtf(__double2float_ru(rad * rad - gap * gap)) * (1.0 + 2e-7) + g.slack;
+    const int ca = cell_coord(q0 - half, g.o0, g.inv_cell, g.d0[0]) >> lv.shift,
+              cb = cell_coord(q0 + half, g.o0, g.inv_cell, g.d0[0]) >> lv.shift;
+    s = __ldg(lv.cs + row * lv.d0 + ca); e = __ldg(lv.cs + row * lv.d0 + cb + 1);
+}
+#ifndef SD_KNN_HEAVY
+#define SD_KNN_HEAVY 192
+#endif
+constexpr int kHeavy = SD_KNN_HEAVY;            // a disc with more candidates than this is swept by the whole warp
+
+#ifndef SD_KNN_MINB
+#define SD_KNN_MINB 1
+#endif
 template <int KS>
-__global__ void __launch_bounds__(kKnnThreads)
+__global__ void __launch_bounds__(kKnnThreads, (KS <= 11 ? SD_KNN_MINB : 1))
 knn_kernel(const KnnJob* __restrict__ jobs) {
     constexpr int K = KS - 1;
-    __shared__ int s_list[kListCap][kKnnThreads];
+    constexpr int KN = K > 0 ? K : 1;
+    using Cfg = KnnCfg<KN>;
+    constexpr int kListCap = Cfg::list_cap;
+    extern __shared__ int2 s_dyn[];
+    int2 (*s_seg)[kKnnThreads] = reinterpret_cast<int2 (*)[kKnnThreads]>(s_dyn);                   // (start, end) of a row run
+    int (*s_list)[kKnnThreads] = reinterpret_cast<int (*)[kKnnThreads]>(s_dyn + kMaxRows * kKnnThreads);   // candidate indices
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const int keff = min(J.k, g.n);
+    const int need = min(Cfg::min_fed, g.n);
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     const int tid = threadIdx.x;
     U128 acc_sum{0ull, 0ull}, acc_sq{0ull, 0ull};
     unsigned long long acc_pos = 0ull;
-
-    // warps claim 32 consecutive (cell-sorted) queries at a time from a per-job counter: sparse-region
-    // queries cost 10-100x more than dense ones, static partitioning left half of the SMs idle at the end
+    // warps claim 32 consecutive (cell-sorted) queries at a time from a per-job counter
     while (true) {
         int wbase = 0;
         if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
         wbase = __shfl_sync(SD_FULL, wbase, 0);
         if (wbase >= g.n) break;
-        const int i = wbase + lane_id();
-        if (i >= g.n) continue;
-        const float qx = __ldg(J.sx + i), qy = __ldg(J.sy + i), qz = __ldg(J.sz + i);
+        const bool valid = wbase + lane_id() < g.n;              // lanes past the end shadow the last query (warp stays converged)
+        const int i = valid ? wbase + lane_id() : g.n - 1;
+        const float4 qp = __ldg(J.sp + i);
+        const float qx = qp.x, qy = qp.y, qz = qp.z;
         const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
-        const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1);
-        // ---- phase 1
-        FNet<KS> net; net.init();
-        int rold = -1, r = 1;
-        for (;; r <<= 1) {
-            for_new_segments(J, g, c0, c1, r, rold, [&](int s, int e) {
-                for (int j = s; j < e; ++j) net.feed(key_f32(J, j, qx, qy, qz));
-            });
-            const int lo0 = c0 - r, hi0 = c0 + r, lo1 = c1 - r, hi1 = c1 + r;
-            const double e_lo0 = (lo0 <= 0) ? inf : q0 - (g.o0 + (double)lo0 * g.cell);
-            const double e_hi0 = (hi0 >= g.d0 - 1) ? inf : (g.o0 + (double)(hi0 + 1) * g.cell) - q0;
-            const double e_lo1 = (lo1 <= 0) ? inf : q1 - (g.o1 + (double)lo1 * g.cell);
-            const double e_hi1 = (hi1 >= g.d1 - 1) ? inf : (g.o1 + (double)(hi1 + 1) * g.cell) - q1;
-            double lb = fmin(fmin(e_lo0, e_hi0), fmin(e_lo1, e_hi1));
-            if (lb == inf) break;                       // the square covers the whole grid
-            lb = lb - g.slack;
-            // every unvisited point is at least lb away: stop when the k-th key (inflated by its error) is closer
-            if (lb > 0.0 && keff > 0 && (double)net.get(keff - 1) * 1.000002 <= lb * lb) break;
-            rold = r;
-        }
-        // ---- phase 2
-        const float wk = (keff > 0) ? net.get(keff - 1) : 0.f;
-        const float band = wk * (1.0f + 4.0f * kKeyErr);
-        int cnt = 0;
-        for_new_segments(J, g, c0, c1, r, -1, [&](int s, int e) {
-            for (int j = s; j < e; ++j) {
-                const bool in = key_f32(J, j, qx, qy, qz) <= band;
-                if (in && cnt < kListCap) s_list[cnt][tid] = j;
-                cnt += in ? 1 : 0;
+        const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
+        // ---- sampling level: finest one with at least k + 2 points in the 3x3 cells (all levels are probed at once)
+        int s3[3], e3[3], L = 0, tot3 = 0;
+        {
+            int sa[kLevels][3], ea[kLevels][3], tot[kLevels];
+#pragma unroll
+            for (int l = 0; l < kLevels; ++l) tot[l] = block3_runs(J, g, l, c0, c1, sa[l], ea[l]);
+            L = kLevels - 1;
+#pragma unroll
+            for (int l = kLevels - 2; l >= 0; --l) if (tot[l] >= need) L = l;
+            tot3 = tot[0];
+#pragma unroll
+            for (int l = 1; l < kLevels; ++l) if (l == L) tot3 = tot[l];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                s3[t] = sa[0][t]; e3[t] = ea[0][t];
+#pragma unroll
+                for (int l = 1; l < kLevels; ++l) if (l == L) { s3[t] = sa[l][t]; e3[t] = ea[l][t]; }
             }
-        });
+        }
+        // ---- phase 1: upper bound of the k-th squared distance from the nearest cells
+        FNet<KN> net; net.init();
+        int fed = 0;
+        {
+            // few points in the 3x3 cells: all of them; otherwise three windows: own row centred on the query's
+            // cell (on the query itself at level 0), adjacent rows centred on their run
+            int ws[3], we[3];
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const int win = (tot3 <= Cfg::feed_all) ? (e3[t] - s3[t]) : ((t == 0) ? Cfg::own_win : Cfg::side_win);
+                int mid = (s3[t] + e3[t]) >> 1;
+                if (t == 0 && L == 0) mid = i;
+                const int a = max(s3[t], min(mid - win / 2, e3[t] - win));
+                ws[t] = a; we[t] = min(e3[t], a + win);
+            }
+            const int n0 = we[0] - ws[0], n1 = we[1] - ws[1], n2 = we[2] - ws[2];
+            fed = n0 + n1 + n2;
+            for (int t0 = 0; t0 < fed; t0 += kBatch) {            // flattened over the three windows, kBatch loads in flight
+                float4 c[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    const int t = min(t0 + u, fed - 1);
+                    const int j = (t < n0) ? ws[0] + t : ((t < n0 + n1) ? ws[1] + (t - n0) : ws[2] + (t - n0 - n1));
+                    c[u] = __ldg(J.sp + j);
+                }
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    net.feed((t0 + u < fed) ? key_of(c[u], qx, qy, qz) : __int_as_float(0x7f800000));
+            }
+            if (fed < need) {                                     // sparse even at the coarsest level: grow rings there
+                const LevelRt lv = level_of(J, g, L);
+                const int k0 = c0 >> lv.shift, k1 = c1 >> lv.shift;
+                net.init(); fed = 0;
+                int rold = -1;
+                for (int r = 1;; r += max(1, r >> 2)) {
+                    for_new_segments(lv, k0, k1, r, rold, [&](int s, int e) {
+                        const int e2 = min(e, s + (Cfg::feed_cap - fed));
+                        for (int j = s; j < e2; ++j) net.feed(key_f32(J, j, qx, qy, qz));
+                        fed += max(e2 - s, 0);
+                    });
+                    if (fed >= need) break;
+                    if (k0 - r <= 0 && k0 + r >= lv.d0 - 1 && k1 - r <= 0 && k1 + r >= lv.d1 - 1) break;   // whole grid seen
+                    rold = r;
+                }
+            }
+        }
+        // ---- phase 2: collect everything inside the bound.  Lanes with an ordinary disc sweep it themselves;
+        //      a lane whose disc holds many candidates (an outlier above / below a dense region: the grid is 2-D)
+        //      is served by the whole warp, 32 candidates per step.  A list overflow tightens the bound from the
+        //      listed keys and sweeps again.
+        int cnt = 0;
+        {
+            bool todo = (keff > 0 && fed >= keff);
+            float band = todo ? net.get(keff - 1) * (1.0f + 4.0f * kKeyErr) : 0.f;
+            for (int attempt = 0;; ++attempt) {
+                const double rad = sqrt((double)band) * (1.0 + 1e-9) + g.slack;
+                // sweep level: the finest one on which the disc spans at most 7 rows
+                int Ls = kLevels - 1;
+#pragma unroll
+                for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(3 << (2 * l))) Ls = l;
+                const LevelRt lv = level_of(J, g, Ls);
+                const int k1 = c1 >> lv.shift;
+                const int R = (int)(rad * lv.inv_cell) + 1;
+                const int rlo = max(k1 - R, 0), rhi = min(k1 + R, lv.d1 - 1);
+                int nruns = 0, total = 0;
+                bool heavy = false;
+                if (todo) {
+                    if (rhi - rlo < kMaxRows) {
+                        for (int row = rlo; row <= rhi; ++row) {
+                            int s, e; row_run(g, lv, q0, q1, rad, k1, row, s, e);
+                            if (e > s) { s_seg[nruns][tid] = make_int2(s, e); ++nruns; total += e - s; }
+                        }
+                        heavy = total > kHeavy;
+                    } else heavy = true;
+                }
+                if (todo) cnt = 0;
+                if (todo && !heavy) {
+                    for (int ri = 0; ri < nruns; ++ri) {
+                        const int2 se = s_seg[ri][tid];
+                        for (int j0 = se.x; j0 < se.y; j0 += kBatch) {
+                            float4 c[kBatch];
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) c[u] = __ldg(J.sp + min(j0 + u, se.y - 1));
+#pragma unroll
+                            for (int u = 0; u < kBatch; ++u) {
+                                const bool in = (j0 + u < se.y) && key_of(c[u], qx, qy, qz) <= band;
+                                if (in && cnt < kListCap) s_list[cnt][tid] = j0 + u;
+                                cnt += in ? 1 : 0;
+                            }
+                        }
+                    }
+                }
+                // heavy lanes, one after the other, all 32 lanes on each
+                for (unsigned hm = __ballot_sync(SD_FULL, todo && heavy); hm; hm &= hm - 1) {
+                    const int ld = __ffs(hm) - 1;
+                    const float hx = __shfl_sync(SD_FULL, qx, ld), hy = __shfl_sync(SD_FULL, qy, ld), hz = __shfl_sync(SD_FULL, qz, ld);
+                    const float hband = __shfl_sync(SD_FULL, band, ld);
+                    const double h0 = __shfl_sync(SD_FULL, q0, ld), h1 = __shfl_sync(SD_FULL, q1, ld), hrad = __shfl_sync(SD_FULL, rad, ld);
+                    const int hLs = __shfl_sync(SD_FULL, Ls, ld), hk1 = __shfl_sync(SD_FULL, k1, ld);
+                    const int hrlo = __shfl_sync(SD_FULL, rlo, ld), hrhi = __shfl_sync(SD_FULL, rhi, ld);
+                    const int htid = (tid & ~31) + ld;
+                    const LevelRt hv = level_of(J, g, hLs);
+                    int hcnt = 0;
+                    for (int row0 = hrlo; row0 <= hrhi; row0 += 32) {
+                        int ms = 0, me = 0;
+                        if (row0 + lane_id() <= hrhi) row_run(g, hv, h0, h1, hrad, hk1, row0 + lane_id(), ms, me);
+                        const int nr = min(32, hrhi - row0 + 1);
+                        for (int r = 0; r < nr; ++r) {
+                            const int s = __shfl_sync(SD_FULL, ms, r), e = __shfl_sync(SD_FULL, me, r);
+                            for (int j0 = s; j0 < e; j0 += 32) {
+                                const int j = j0 + lane_id();
+                                const bool in = (j < e) && key_of(__ldg(J.sp + min(j, e - 1)), hx, hy, hz) <= hband;
+                                const unsigned bm = __ballot_sync(SD_FULL, in);
+                                const int slot = hcnt + __popc(bm & ((1u << lane_id()) - 1u));
+                                if (in && slot < kListCap) s_list[slot][htid] = j;
+                                hcnt += __popc(bm);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane_id() == ld) cnt = hcnt;
+                }
+                // overflow: the k-th smallest of the listed kListCap (>= k) keys is a tighter bound
+                todo = todo && cnt > kListCap && attempt < 3;
+                if (!__any_sync(SD_FULL, todo)) break;
+                if (todo) {
+                    net.init();
+                    for (int e = 0; e < kListCap; ++e) net.feed(key_f32(J, s_list[e][tid], qx, qy, qz));
+                    band = fminf(band, net.get(keff - 1) * (1.0f + 4.0f * kKeyErr));
+                }
+            }
+        }
         // ---- phase 3
         double sum;
         if (cnt > kListCap || cnt < keff) {
-            sum = knn_exact_sum<(K > 0 ? K : 1)>(J, g, qx, qy, qz, q0, q1, c0, c1, keff);
+            sum = knn_exact_sum<KN>(J, g, qx, qy, qz, q0, q1, c0, c1, keff);
         } else {
-            double bd[K > 0 ? K : 1];
+            UNetK<KN + 1> un; un.init();
+            for (int e0 = 0; e0 < cnt; e0 += kBatch) {
+                float4 c[kBatch];
 #pragma unroll
-            for (int p = 0; p < K; ++p) bd[p] = inf;
-            for (int e = 0; e < cnt; ++e) {
-                const int j = s_list[e][tid];
-                const double dx = (double)__ldg(J.sx + j) - (double)qx, dy = (double)__ldg(J.sy + j) - (double)qy,
-                             dz = (double)__ldg(J.sz + j) - (double)qz;
-                double v = (dx * dx + dy * dy) + dz * dz;
+                for (int u = 0; u < kBatch; ++u) c[u] = __ldg(J.sp + s_list[min(e0 + u, cnt - 1)][tid]);
 #pragma unroll
-                for (int p = 0; p < K; ++p) { const double lo = fmin(bd[p], v); v = fmax(bd[p], v); bd[p] = lo; }
+                for (int u = 0; u < kBatch; ++u) {
+                    const uint32_t kb = __float_as_uint(key_of(c[u], qx, qy, qz));
+                    un.feed((e0 + u < cnt) ? (((kb >> kSlotBits) << kSlotBits) | (uint32_t)(e0 + u)) : 0xffffffffu);
+                }
             }
+            double bd[KN];
+            bool ok = true;
             sum = 0.0;
 #pragma unroll
-            for (int p = 0; p < K; ++p) if (p < keff) sum = sum + sqrt(bd[p]);
+            for (int p0 = 0; p0 < K; p0 += kBatch) {              // the winners, kBatch loads in flight
+                float4 w[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u)
+                    if (p0 + u < K) w[u] = __ldg(J.sp + s_list[(p0 + u < keff) ? (un.d[p0 + u] & ((1u << kSlotBits) - 1u)) : 0][tid]);
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) {
+                    if (p0 + u < K) {
+                        const int p = p0 + u;
+                        bd[p] = inf;
+                        if (p < keff) {
+                            bd[p] = dist2_of(w[u], qx, qy, qz);
+                            if (p > 0) ok = ok && (bd[p - 1] <= bd[p]);
+                            sum = sum + sqrt(bd[p]);
+                        }
+                    }
+                }
+            }
+            // membership is certain when the (k+1)-th truncated key is at least two cells above the k-th
+            const uint32_t ka = un.get(keff - 1) >> kSlotBits, kb1 = un.get(keff) >> kSlotBits;
+            ok = ok && (cnt == keff || kb1 >= ka + 2u);
+            if (!ok) {                                            // near tie: exact selection over the whole list
+#pragma unroll
+                for (int p = 0; p < K; ++p) bd[p] = inf;
+                for (int e = 0; e < cnt; ++e) {
+                    double v = dist2_f64(J, s_list[e][tid], qx, qy, qz);
+#pragma unroll
+                    for (int p = 0; p < K; ++p) { const double lo = fmin(bd[p], v); v = fmax(bd[p], v); bd[p] = lo; }
+                }
+                sum = 0.0;
+#pragma unroll
+                for (int p = 0; p < K; ++p) if (p < keff) sum = sum + sqrt(bd[p]);
+            }
         }
         const double avg = (keff > 0) ? sum / (double)keff : -1.0;
-        J.avg[__ldg(J.sorig + i)] = avg;
-        J.savg[i] = avg;
-        if (avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
+        if (valid) J.avg[__float_as_int(qp.w)] = avg;
+        if (valid && avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
     }
 
     // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums.
@@ -401,19 +713,45 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// 3b. statistical filter applied to the sorted copies of every level: dead points get x = +inf, so every
+//     later distance test against them fails without a second lookup (the radius kernel reads x anyway)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGridThreads)
+sor_mark_kernel(const KnnJob* __restrict__ jobs) {
+    const KnnJob J = jobs[blockIdx.y];
+    if (!J.use_sor) return;
+    const int n = J.gs->n;
+    const double thr = J.stats[2];
+    int alive_local = 0;
+    for (int p = blockIdx.x * kGridThreads + threadIdx.x; p < kLevels * n; p += gridDim.x * kGridThreads) {
+        const int orig = __float_as_int(J.sp[p].w);
+        const double a = J.avg[orig];
+        const bool alive = (a > 0.0 && a < thr);
+        if (!alive) J.sp[p].x = __int_as_float(0x7f800000);
+        if (p < n) { if (!alive) J.cnt[orig] = 0; alive_local += alive ? 1 : 0; }
+    }
+    alive_local = warp_sum(alive_local);
+    if (lane_id() == 0 && J.n_alive && alive_local) atomicAdd(J.n_alive, alive_local);
+}
+
+// ---------------------------------------------------------------------------------------------
 // 4. radius count with early exit (Open3D RemoveRadiusOutliers, per point)
 // ---------------------------------------------------------------------------------------------
+// With the statistical filter on, sor_mark_kernel has already moved the dead points to x = +inf.
+// Level: the finest one whose 3x3 cells around the query hold more than `cap` points (dense regions: the
+// walk stops after ~cap tests right around the query); sparse regions count at the coarsest level whose
+// cells are still no larger than the radius, where the radius spans few rows.
 __global__ void __launch_bounds__(kKnnThreads)
 radius_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const double r = J.radius, r2 = r * r;
     const float r2_in = __double2float_rd(r2 * (1.0 - 3e-6)), r2_out = __double2float_ru(r2 * (1.0 + 3e-6));
-    const bool sor = J.use_sor != 0;
-    const double thr = sor ? J.stats[2] : 0.0;
     const int cap = J.count_cap;
-    const int rows = (int)ceil(r * g.inv_cell) + 1;
-    int alive_local = 0;
+    const float finf = __int_as_float(0x7f800000);
+    int Lmax = 0;
+#pragma unroll
+    for (int l = 1; l < kLevels; ++l) if (g.cell * (double)(1 << (2 * l)) <= r) Lmax = l;
     while (true) {
         int wbase = 0;
         if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
@@ -421,63 +759,66 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
         if (wbase >= g.n) break;
         const int i = wbase + lane_id();
         if (i >= g.n) continue;
-        const int orig = __ldg(J.sorig + i);
-        if (sor) {
-            const double a = J.savg[i];
-            if (!(a > 0.0 && a < thr)) { J.cnt[orig] = 0; continue; }
-            ++alive_local;
-        }
-        const float qx = __ldg(J.sx + i), qy = __ldg(J.sy + i), qz = __ldg(J.sz + i);
+        const float4 qp = __ldg(J.sp + i);
+        const float qx = qp.x, qy = qp.y, qz = qp.z;
+        if (qx == finf) continue;                               // removed by the statistical filter (count already 0)
         const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
-        const int c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1);
+        const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
+        int L = Lmax;
+        if (cap >= 0) {
+            int s3[3], e3[3];
+#pragma unroll
+            for (int l = kLevels - 2; l >= 0; --l) if (l < Lmax) { if (block3_runs(J, g, l, c0, c1, s3, e3) > cap) L = l; }
+        }
+        const LevelRt lv = level_of(J, g, L);
+        const int k0 = c0 >> lv.shift, k1 = c1 >> lv.shift;
+        const int rows = (int)ceil(r * lv.inv_cell) + 1;
         int count = 0;
         bool done = false;
         for (int t = 0; t <= 2 * rows && !done; ++t) {
             const int dr = (t == 0) ? 0 : ((t & 1) ? (t + 1) / 2 : -(t / 2));
-            const int row = c1 + dr;
-            if (row < 0 || row >= g.d1) continue;
+            const int row = k1 + dr;
+            if (row < 0 || row >= lv.d1) continue;
             double gap = 0.0;                                // distance from q to the row's slab along a1
-            if (dr > 0) gap = (g.o1 + (double)row * g.cell) - q1;
-            else if (dr < 0) gap = q1 - (g.o1 + (double)(row + 1) * g.cell);
+            if (dr > 0) gap = (g.o1 + (double)row * lv.cell) - q1;
+            else if (dr < 0) gap = q1 - (g.o1 + (double)(row + 1) * lv.cell);
             gap -= g.slack;
             if (gap > r) continue;
             if (gap < 0.0) gap = 0.0;
-            const double half = sqrt(r2 - gap * gap) + g.slack;
-            const int ca = cell_coord(q0 - half, g.o0, g.inv_cell, g.d0), cb = cell_coord(q0 + half, g.o0, g.inv_cell, g.d0);
-            const int rb = row * g.d0;
-            const int s = J.cell_start[rb + ca], e = J.cell_start[rb + cb + 1];
-            // walk outwards from the query's own position (its own index in its row, the cell straight
-            // above / below it in the other rows): near candidates first, so dense queries stop after ~cap tests
-            const int c0q = cell_coord(q0, g.o0, g.inv_cell, g.d0);
-            int mid = (dr == 0) ? i : J.cell_start[rb + c0q];
+            const double half = (double)sqrtf(__double2float_ru(r2 - gap * gap)) * (1.0 + 2e-7) + g.slack;
+            const int ca = cell_coord(q0 - half, g.o0, g.inv_cell, g.d0[0]) >> lv.shift,
+                      cb = cell_coord(q0 + half, g.o0, g.inv_cell, g.d0[0]) >> lv.shift;
+            const int rb = row * lv.d0;
+            const int s = __ldg(lv.cs + rb + ca), e = __ldg(lv.cs + rb + cb + 1);
+            if (s >= e) continue;
+            // walk outwards from the query's own position (its own index in its row at level 0, the start of
+            // the cell straight above / below it otherwise), four candidates per side and step: near
+            // candidates first, so dense queries stop after ~cap tests, and eight independent loads are in flight
+            int mid = (dr == 0 && L == 0) ? i : __ldg(lv.cs + rb + k0);
             mid = min(max(mid, s), e);
-            auto test = [&](int j) {
-                const float px = __ldg(J.sx + j), py = __ldg(J.sy + j), pz = __ldg(J.sz + j);
-                const float fx = px - qx, fy = py - qy, fz = pz - qz;
-                const float d2f = (fx * fx + fy * fy) + fz * fz;       // fp32 pre-test, relative error < 1.5e-6
-                if (d2f > r2_out) return;
-                bool in = d2f < r2_in;
-                if (!in) {
-                    const double dx = (double)px - (double)qx, dy = (double)py - (double)qy, dz = (double)pz - (double)qz;
-                    in = ((dx * dx + dy * dy) + dz * dz) <= r2;
-                }
-                if (in && sor) { const double a = J.savg[j]; in = (a > 0.0 && a < thr); }
-                if (in) {
-                    ++count;
-                    if (cap >= 0 && count > cap) done = true;
-                }
-            };
             int jl = mid - 1, jr = mid;
             while (!done && (jl >= s || jr < e)) {
-                if (jr < e) { test(jr); ++jr; }
-                if (!done && jl >= s) { test(jl); --jl; }
+                float4 c[8]; bool ok[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = (u < 4) ? jr + u : jl - (u - 4);
+                    ok[u] = (u < 4) ? (j < e) : (j >= s);
+                    c[u] = __ldg(J.sp + (ok[u] ? j : i));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float d2f = key_of(c[u], qx, qy, qz);             // fp32 pre-test, relative error < 1.5e-6
+                    bool in = d2f < r2_in;
+                    if (!in && d2f <= r2_out) in = dist2_of(c[u], qx, qy, qz) <= r2;   // inside the error band: decide in fp64
+                    count += (ok[u] && in) ? 1 : 0;
+                }
+                jr += 4; jl -= 4;
+                done = (cap >= 0 && count > cap);
             }
         }
-        J.cnt[orig] = count;
+        J.cnt[__float_as_int(qp.w)] = (cap >= 0 && count > cap) ? cap + 1 : count;
     }
-    alive_local = warp_sum(alive_local);
     if (lane_id() == 0) {
-        if (sor && J.n_alive && alive_local) atomicAdd(J.n_alive, alive_local);
         __threadfence();
         if (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * (kKnnThreads / 32) - 1) { J.gs->ticket = 0; J.gs->work = 0; }
     }
@@ -505,23 +846,42 @@ int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStrea
     return SD_OK;
 }
 
+template <int KS>
+static int launch_knn_t(const sd::KnnJob* d_jobs, dim3 grid, cudaStream_t st) {
+    using namespace sd;
+    constexpr size_t smem = KnnCfg<(KS > 1 ? KS - 1 : 1)>::smem_bytes;
+    static bool configured = false;       // per instantiation; the attribute is per function
+    if (!configured) {
+        SD_CUDA_TRY(cudaFuncSetAttribute(knn_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    knn_kernel<KS><<<grid, kKnnThreads, smem, st>>>(d_jobs);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st) {
     using namespace sd;
     if (njobs <= 0) return SD_OK;
     if (k < 1 || k > kMaxKnnK) return SD_ERR_INVALID;
     dim3 grid = grid_for(cap, kKnnThreads, 1, njobs, 16);   // <= kKnnMaxBlocks CTAs per job
-    if (k <= 3) knn_kernel<4><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 7) knn_kernel<8><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 10) knn_kernel<11><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 16) knn_kernel<17><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 20) knn_kernel<21><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else if (k <= 32) knn_kernel<33><<<grid, kKnnThreads, 0, st>>>(d_jobs);
-    else knn_kernel<65><<<grid, kKnnThreads, 0, st>>>(d_jobs);
+    if (k <= 3) return launch_knn_t<4>(d_jobs, grid, st);
+    if (k <= 7) return launch_knn_t<8>(d_jobs, grid, st);
+    if (k <= 10) return launch_knn_t<11>(d_jobs, grid, st);
+    if (k <= 16) return launch_knn_t<17>(d_jobs, grid, st);
+    if (k <= 20) return launch_knn_t<21>(d_jobs, grid, st);
+    if (k <= 32) return launch_knn_t<33>(d_jobs, grid, st);
+    return launch_knn_t<65>(d_jobs, grid, st);
+}
+
+// cloud statistics are folded into knn_kernel; this applies the resulting threshold to the sorted copies
+int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st) {
+    using namespace sd;
+    if (njobs <= 0) return SD_OK;
+    sor_mark_kernel<<<grid_for(3 * cap, kGridThreads, 4, njobs, 8), kGridThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
-
-int sd_launch_sor_stats(const sd::KnnJob*, int, cudaStream_t) { return SD_OK; }   // folded into knn_kernel
 
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st) {
     using namespace sd;

@@ -11,9 +11,11 @@ independent (frame-parallel, weak scaling, no collective on the data path).  One
   value     frames/s with the inputs already resident in HBM (CUDA events, max over ranks)
   e2e       frames/s through the host-facing API: pinned host inputs, H2D + fused path + D2H of the
             answers inside the timed region
-  roofline  the pixel-stage kernel (the HBM-bound kernel of the path): algorithmic bytes per launch /
-            its mean device time measured with CUDA events inside the timed region, vs the measured
-            HBM peak of MEASURED_PEAKS.json; roofline_path = the whole path's SURVEY 8d B_alg figure
+  roofline  the dominant kernel of the step (sd::knn_kernel, the statistical filter's neighbour search;
+            share in profiles/): SURVEY 8d's algorithmic bytes of that stage per launch / its mean device
+            time measured with CUDA events inside the timed region, vs the measured HBM peak of
+            MEASURED_PEAKS.json.  roofline_pixel = the same for the HBM-streaming pixel stage;
+            roofline_path = the whole path's SURVEY 8d B_alg figure x frames/s
   cpu_baseline / --impl reference   the oracle port of the reference's CPU path on the host cores
 """
 from __future__ import annotations
@@ -204,7 +206,7 @@ def run_b200(a):
     for b in range(nb):
         for tag, res in pipe.warm_device(d_logits[b], d_disp[b], intr, tag=b):
             expected.setdefault(tag, res)
-    pipe.pixel_ms.clear(); pipe.total_ms.clear()
+    pipe.pixel_ms.clear(); pipe.knn_ms.clear(); pipe.total_ms.clear()
 
     def run_device_steps(n, check):
         bad = 0
@@ -219,7 +221,7 @@ def run_b200(a):
 
     # ---- warm-up, then the timed region (device-resident inputs)
     run_device_steps(a.warmup, False)
-    pipe.pixel_ms.clear(); pipe.total_ms.clear()
+    pipe.pixel_ms.clear(); pipe.knn_ms.clear(); pipe.total_ms.clear()
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -239,6 +241,7 @@ def run_b200(a):
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
     pixel_ms = list(pipe.pixel_ms)
+    knn_ms = list(pipe.knn_ms)
     total_ms = list(pipe.total_ms)
 
     # ---- end to end: pinned host inputs -> H2D -> fused path -> D2H of the answers, pipelined over the slots
@@ -291,22 +294,33 @@ def run_b200(a):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
         counts0 = expected[0].counts(0)
         # pixel-stage kernel: algorithmic bytes per launch = sum over the batch of 20*HW + 12*(N_R0+N_F0)
-        per_batch_pixel_bytes = []
-        per_batch_alg = []
+        per_batch_pixel_bytes, per_batch_knn_bytes, per_batch_alg = [], [], []
         for b in range(nb):
             r = expected[b]
-            pb = sum(20.0 * HW + 12.0 * (r.counts(f)["road_gather"] + r.counts(f)["fence_gather"]) for f in range(B))
-            per_batch_pixel_bytes.append(pb)
-            per_batch_alg.append(sum(b_alg_bytes(r.counts(f), HW) for f in range(B)))
+            cs = [r.counts(f) for f in range(B)]
+            per_batch_pixel_bytes.append(sum(20.0 * HW + 12.0 * (c["road_gather"] + c["fence_gather"]) for c in cs))
+            # statistical_outlier_removal stage of SURVEY 8d: 12 B per point in + 12 B per surviving point out
+            per_batch_knn_bytes.append(sum(12.0 * (c["road_plane"] + c["road_sor"]) for c in cs))
+            per_batch_alg.append(sum(b_alg_bytes(c, HW) for c in cs))
         pix_bytes = float(np.mean(per_batch_pixel_bytes))
+        knn_bytes = float(np.mean(per_batch_knn_bytes))
         pix_ms = float(np.mean(pixel_ms)) if pixel_ms else float("nan")
-        achieved = pix_bytes / (pix_ms * 1e-3) / 1e9 if pix_ms == pix_ms and pix_ms > 0 else None
-        traffic = None
+        k_ms = float(np.mean(knn_ms)) if knn_ms else float("nan")
+
+        def gbs(nbytes, ms):
+            return nbytes / (ms * 1e-3) / 1e9 if ms == ms and ms > 0 else None
+
+        prof = {}
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "pixel_fuse_ncu.json")))
-            traffic = prof.get("dram_bytes_per_launch")
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
         except Exception:
             pass
+
+        def traffic_of(kernel):
+            t = prof.get(kernel, {}).get("dram_bytes_per_launch")
+            return float(t) if t is not None else None
+
+        knn_ach, pix_ach = gbs(knn_bytes, k_ms), gbs(pix_bytes, pix_ms)
         frames = a.steps * B * world
         value = frames / (elapsed_ms * 1e-3)
         alg_path = float(np.mean(per_batch_alg)) / B
@@ -327,10 +341,17 @@ def run_b200(a):
             "host_wall_ms": wall * 1e3,
             "batch_latency_ms": {"mean": float(np.mean(total_ms)) if total_ms else None,
                                  "note": "first to last kernel of one batch, CUDA events, while other batches overlap"},
-            "roofline": {"kernel": "sd::pixel_fuse_kernel", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": (achieved / peak_gbs) if achieved else None, "traffic": traffic,
-                         "algorithmic_bytes_per_launch": pix_bytes, "kernel_ms": pix_ms, "peak_source": peak_src,
-                         "note": "kernel time measured concurrently with other batches' kernels (pipelined run)"},
+            "roofline": {"kernel": "sd::knn_kernel<11> (dominant kernel of the step, profiles/r1_launches.csv)", "bound": "hbm",
+                         "achieved": knn_ach, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": (knn_ach / peak_gbs) if knn_ach else None, "traffic": traffic_of("knn_kernel"),
+                         "algorithmic_bytes_per_launch": knn_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
+                         "note": "exact k-NN on an L1/L2-resident cloud: bound by instruction issue and cache latency, not by "
+                                 "HBM (DESIGN.md 3); kernel time measured with CUDA events while other batches' kernels run"},
+            "roofline_pixel": {"kernel": "sd::pixel_label_kernel + pixel_scan_kernel + pixel_scatter_kernel", "bound": "hbm",
+                               "achieved": pix_ach, "peak": peak_gbs, "unit": "GB/s",
+                               "frac": (pix_ach / peak_gbs) if pix_ach else None, "traffic": traffic_of("pixel_stage"),
+                               "algorithmic_bytes_per_launch": pix_bytes, "kernel_ms": pix_ms,
+                               "note": "pixel stage (3 kernels) timed as one segment, concurrently with other batches"},
             "roofline_path": {"bound": "hbm", "algorithmic_bytes_per_frame": alg_path,
                               "achieved": alg_path * value / world / 1e9, "peak": peak_gbs, "unit": "GB/s",
                               "frac": alg_path * value / world / 1e9 / peak_gbs,

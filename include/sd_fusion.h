@@ -253,16 +253,16 @@ int sd_fuse_frames_host(const float* h_logits, const float* h_disp, int batch, i
  * being captured into a CUDA graph).  sd_ws_stage_elapsed_ms: which = 0 pixel-stage kernel,
  * 1 = whole fused call; the stream must have been synchronised past the call. */
 int sd_ws_enable_timing(SdWorkspace* ws, int enable);
-/* Restrict the next sd_fuse_frames calls to a subset of the path: bit 0 = pixel stage, bit 1 = cloud
- * stages + answers (default 3 = everything).  Lets a caller capture the two halves into separate CUDA
- * graphs and time the pixel-stage kernel with its own events (events recorded inside a captured graph
- * cannot be used with cudaEventElapsedTime). */
+/* Restrict the next sd_fuse_frames calls to a subset of the path (default 15 = everything):
+ *   bit 0 = pixel stage; bit 1 = cloud stages up to the neighbour-search grid, and the whole fence chain;
+ *   bit 2 = the k-NN kernel of the statistical filter; bit 3 = radius search, final road compaction,
+ *   slab and answers.  Lets a caller capture the segments into separate CUDA graphs and bracket a
+ *   kernel with its own events (events recorded inside a captured graph cannot be timed). */
 int sd_ws_set_stage_mask(SdWorkspace* ws, int mask);
 int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms);
 
-/* Developer counters of the organized neighbour search of `frame` (cumulative since sd_ws_create):
- * k-NN queries, queued hard k-NN queries, window-certificate failures, ray-bound failures, list overflows,
- * -, queued hard radius queries, sum of per-query candidate-list lengths.  Synchronises the device. */
+/* Developer counters of the neighbour search of `frame` (cumulative since sd_ws_create; all zero unless the
+ * library was built with -DSD_KNN_STATS).  Synchronises the device. */
 int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8);
 
 /* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):

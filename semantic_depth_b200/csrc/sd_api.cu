@@ -83,7 +83,7 @@ struct FusedTables {
     CompactJob* c_road_y; CompactJob* c_road_x; CompactJob* c_road_plane; CompactJob* c_road_final;
     CompactJob* c_fence_y; CompactJob* c_fence_z; CompactJob* c_split; CompactJob* c_side_x; CompactJob* c_side_plane;
     PlaneJob* p_road; PlaneJob* p_side;
-    MeanJob* m_fence; SlabJob* s_road; KnnJob* k_road; FinalJob* fin; OrgJob* o_road;
+    MeanJob* m_fence; SlabJob* s_road; KnnJob* k_road; FinalJob* fin;
     RansacJob* r_road; RansacJob* r_side;
 };
 
@@ -95,7 +95,6 @@ struct WsPriv {
     SdFrameResult* results;
     SdCamera cam;
     double cell_scale;
-    bool organized;
     cudaEvent_t ev_t[3]; bool timing; int stage_mask;
 };
 
@@ -124,13 +123,8 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->cell_start = c.take<int32_t>(F * ((size_t)ws->cell_cap + 8));
     ws->cell_of = c.take<int32_t>(F * cap);
     ws->sp = c.take<float4>(F * cap * kLevels);
-    ws->avg = c.take<double>(F * cap); ws->savg = c.take<double>(F * cap);
+    ws->avg = c.take<double>(F * cap);
     ws->cnt = c.take<int32_t>(F * cap);
-    ws->knn_part = c.take<double>((size_t)F * kKnnMaxBlocks * 3);
-    ws->dense = c.take<float4>((size_t)F * ws->height * ws->width);
-    ws->ost = c.take<OrgState>(F);
-    ws->queue_knn = c.take<int32_t>(F * cap);
-    ws->queue_ror = c.take<int32_t>(F * cap);
     ws->gstatus = c.take<unsigned long long>((size_t)F * ws->grid_tiles);
     ws->gctl = c.take<ScanCtl>(F);
     const size_t mh = (size_t)(ws->max_hyp > 0 ? ws->max_hyp : 1);
@@ -217,10 +211,9 @@ void fill_knn(KnnJob& j, const float* x, const float* y, const float* z, const i
     j.gs = ws->gs + f;
     j.cell_count = ws->cell_count + oc; j.cell_start = ws->cell_start + oc; j.cell_of = ws->cell_of + o;
     j.sp = ws->sp + o * kLevels;
-    j.avg = ws->avg + o; j.savg = ws->savg + o; j.cnt = ws->cnt + o;
+    j.avg = ws->avg + o; j.cnt = ws->cnt + o;
     j.scan_status = ws->gstatus + (size_t)f * ws->grid_tiles; j.scan_ctl = ws->gctl + f;
     j.cell_cap = ws->cell_cap;
-    j.part = ws->knn_part + (size_t)f * kKnnMaxBlocks * 3;
     j.cell_scale = cell_scale;
     j.count_cap = -1;
 }
@@ -260,8 +253,6 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaMemsetAsync(ws->gstatus, 0, sizeof(unsigned long long) * max_frames * ws->grid_tiles, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->gctl, 0, sizeof(ScanCtl) * max_frames, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->scratch, 0, ws->scratch_bytes, st));
-    SD_CUDA_TRY(cudaMemsetAsync(ws->ost, 0, sizeof(OrgState) * max_frames, st));
-    { int rc_fill = sd_launch_org_fill(ws->dense, (size_t)max_frames * height * width, st); if (rc_fill) return rc_fill; }
     // GridState: bbox keys start at (+max, 0); FrameState slab keys likewise
     {
         std::vector<GridState> g(max_frames);
@@ -295,11 +286,9 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_fork, cudaEventDisableTiming));
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 3; ++i) SD_CUDA_TRY(cudaEventCreate(&pv->ev_t[i]));
-    pv->timing = false; pv->stage_mask = 3;
+    pv->timing = false; pv->stage_mask = 15;
     const char* e = getenv("SD_FUSE_SINGLE_STREAM");
     pv->single_stream = (e && e[0] == '1');
-    const char* sm = getenv("SD_SOR_MODE");
-    pv->organized = (sm && strcmp(sm, "organized") == 0);     // default: world-space grid search
     const char* cs = getenv("SD_KNN_CELL_SCALE");
     pv->cell_scale = cs ? atof(cs) : 0.6;
     if (!(pv->cell_scale > 0.0)) pv->cell_scale = 0.6;
@@ -563,7 +552,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
     SD_ALLOC(c_split, CompactJob, 2 * B); SD_ALLOC(c_side_x, CompactJob, 2 * B); SD_ALLOC(c_side_plane, CompactJob, 2 * B);
     SD_ALLOC(p_road, PlaneJob, B); SD_ALLOC(p_side, PlaneJob, 2 * B);
     SD_ALLOC(m_fence, MeanJob, B); SD_ALLOC(s_road, SlabJob, B); SD_ALLOC(k_road, KnnJob, B); SD_ALLOC(fin, FinalJob, B);
-    SD_ALLOC(r_road, RansacJob, B); SD_ALLOC(r_side, RansacJob, 2 * B); SD_ALLOC(o_road, OrgJob, B);
+    SD_ALLOC(r_road, RansacJob, B); SD_ALLOC(r_side, RansacJob, 2 * B);
 #undef SD_ALLOC
     const size_t mh = (size_t)(ws->max_hyp > 0 ? ws->max_hyp : 1);
     for (int f = 0; f < B; ++f) {
@@ -605,23 +594,6 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
           if (P.use_sor) { p.aux = h_k_road[f].avg; p.p_d = fs->sor_stats + 2; }
           if (P.use_ror) { p.aux2 = h_k_road[f].cnt; }
           fill_compact(h_c_road_final[f], rB, &fs->n[SD_CNT_ROAD_PLANE], rA, &fs->n[SD_CNT_ROAD_ROR], p, ws, f, 0); }
-        // organized (per-pixel) search: the plane filter also writes the survivors into the frame's pixel image,
-        // the final compaction restores its all-inf invariant
-        { OrgJob& o = h_o_road[f]; memset(&o, 0, sizeof(o));
-          o.x = rB.x; o.y = rB.y; o.z = rB.z; o.src = rB.src; o.n = &fs->n[SD_CNT_ROAD_PLANE];
-          o.dense = ws->dense + (size_t)f * ws->height * ws->width; o.st = ws->ost + f;
-          o.avg = h_k_road[f].avg; o.cnt = h_k_road[f].cnt;
-          o.queue_knn = ws->queue_knn + (size_t)f * cap; o.queue_ror = ws->queue_ror + (size_t)f * cap;
-          o.queue_bound = reinterpret_cast<float*>(h_k_road[f].savg);     // the grid path's scratch is free in this mode
-          o.stats = fs->sor_stats; o.n_alive = &fs->n_sor_alive;
-          o.height = ws->height; o.width = ws->width;
-          o.q03 = pv->cam.q03; o.q13 = pv->cam.q13; o.q23 = pv->cam.q23;
-          o.k = P.sor_nb_neighbors; o.std_ratio = P.sor_std_ratio; o.radius = P.ror_radius;
-          o.nb_points = P.ror_nb_points; o.use_sor = P.use_sor;
-          if (pv->organized && P.sor_nb_neighbors <= 32 && (P.use_sor || P.use_ror)) {
-              h_c_road_plane[f].dense = o.dense; h_c_road_plane[f].dense_mode = 1;
-              h_c_road_final[f].dense = o.dense; h_c_road_final[f].dense_mode = 2;
-          } }
         // slab min/max on rA                                               :254-259
         { SlabJob& s = h_s_road[f]; memset(&s, 0, sizeof(s));
           s.x = rA.x; s.z = rA.z; s.n = &fs->n[SD_CNT_ROAD_ROR]; s.lo = P.slab_lo; s.hi = P.slab_hi;
@@ -712,7 +684,10 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap_st);
     const bool timing = pv->timing && cap_st == cudaStreamCaptureStatusNone;
-    const bool do_pixel = (pv->stage_mask & 1) != 0, do_cloud = (pv->stage_mask & 2) != 0;
+    // stage mask: 1 pixel stage | 2 cloud stages up to the neighbour-search grid + the whole fence chain |
+    //             4 the k-NN kernel | 8 radius search, final road compaction, slab, answers
+    const int sm_ = pv->stage_mask;
+    const bool do_pixel = (sm_ & 1) != 0, do_pre = (sm_ & 2) != 0, do_knn = (sm_ & 4) != 0, do_post = (sm_ & 8) != 0;
     // ---- pixel stage: rA <- road (z cut applied), fA <- fence
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[0], st));
     rc = !do_pixel ? SD_OK : sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
@@ -721,9 +696,9 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
                          nullptr, nullptr, nullptr, ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, st);
     if (rc) return rc;
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[1], st));
-    if (!do_cloud) return SD_OK;
+    if (!do_pre && !do_knn && !do_post) return SD_OK;
     cudaStream_t sf = st;    // fence chain stream
-    const bool fork = P.approach_both && !pv->single_stream;
+    const bool fork = do_pre && P.approach_both && !pv->single_stream;
     if (fork) {
         sf = pv->side_stream;
         SD_CUDA_TRY(cudaEventRecord(pv->ev_fork, st));
@@ -731,6 +706,7 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     }
 #define SD_RUN(expr) do { rc = (expr); if (rc) return rc; } while (0)
     // ---- road chain (stream st)
+    if (do_pre) {
     SD_RUN(sd_launch_select_median(T.sel_road_y_med, B, cap, st));
     SD_RUN(sd_launch_select_median(T.sel_road_y_mad, B, cap, st));
     SD_RUN(sd_launch_compact(T.c_road_y, B, cap, st));
@@ -740,20 +716,17 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     if (d_hyp_road) SD_RUN(sd_launch_ransac(T.r_road, B, cap, n_hyp, st));
     SD_RUN(sd_launch_plane(T.p_road, B, cap, st));
     SD_RUN(sd_launch_compact(T.c_road_plane, B, cap, st));
-    if (pv->organized && P.sor_nb_neighbors <= 32) {
-        if (P.use_sor) SD_RUN(sd_launch_org_knn(T.o_road, B, cap, P.sor_nb_neighbors, st));
-        if (P.use_sor && P.use_ror) SD_RUN(sd_launch_org_apply_sor(T.o_road, B, cap, st));
-        if (P.use_ror) SD_RUN(sd_launch_org_ror(T.o_road, B, cap, st));
-    } else {
-        if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
-        if (P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
-        if (P.use_sor && P.use_ror) SD_RUN(sd_launch_sor_stats(T.k_road, B, cap, st));
-        if (P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
+    if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
     }
-    SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
-    SD_RUN(sd_launch_slab(T.s_road, B, cap, st));
+    if (do_knn && P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
+    if (do_post && P.use_sor && P.use_ror) SD_RUN(sd_launch_sor_stats(T.k_road, B, cap, st));
+    if (do_post && P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
+    if (do_post) {
+        SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
+        SD_RUN(sd_launch_slab(T.s_road, B, cap, st));
+    }
     // ---- fence chain (stream sf)
-    if (P.approach_both) {
+    if (do_pre && P.approach_both) {
         SD_RUN(sd_launch_select_median(T.sel_fence_y_med, B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_fence_y_mad, B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_fence_y, B, cap, sf));
@@ -767,11 +740,11 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
         SD_RUN(sd_launch_plane(T.p_side, 2 * B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_side_plane, 2 * B, cap, sf));
     }
-    if (fork) {
+    if (fork) {     // joins before the answers (or at the end of this call when the path is split across calls)
         SD_CUDA_TRY(cudaEventRecord(pv->ev_join, sf));
         SD_CUDA_TRY(cudaStreamWaitEvent(st, pv->ev_join, 0));
     }
-    SD_RUN(sd_launch_finalize(T.fin, B, &P, st));
+    if (do_post) SD_RUN(sd_launch_finalize(T.fin, B, &P, st));
 #undef SD_RUN
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[2], st));
     return SD_OK;
@@ -782,18 +755,10 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     const int sel = 3, ransac = with_ransac ? 3 : 0;
     int n = 3;                                   // pixel stage: label, scan, scatter
     n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
-    const char* sm = getenv("SD_SOR_MODE");
-    const bool organized = (sm && strcmp(sm, "organized") == 0) && P->sor_nb_neighbors <= 32;
-    if (organized) {
-        if (P->use_sor) n += 2;                  // k-NN main + hard
-        if (P->use_sor && P->use_ror) n += 1;    // apply the statistical filter to the pixel image
-        if (P->use_ror) n += 2;                  // radius main + hard
-    } else {
-        if (P->use_sor || P->use_ror) n += 4;    // grid: bbox, count, scan, scatter
-        if (P->use_sor) n += 1;
-        if (P->use_sor && P->use_ror) n += 1;    // statistical filter applied to the cell-sorted copy
-        if (P->use_ror) n += 1;
-    }
+    if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
+    if (P->use_sor) n += 1;
+    if (P->use_sor && P->use_ror) n += 1;        // statistical filter applied to the cell-sorted copies
+    if (P->use_ror) n += 1;
     n += 1 + 1;                                  // final road compaction, slab
     if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain
     n += 1;                                      // finalize
@@ -824,7 +789,7 @@ extern "C" int sd_ws_enable_timing(SdWorkspace* ws, int enable) {
 }
 
 extern "C" int sd_ws_set_stage_mask(SdWorkspace* ws, int mask) {
-    if (!ws || mask < 1 || mask > 3) return fail(SD_ERR_INVALID, "sd_ws_set_stage_mask: mask must be 1, 2 or 3");
+    if (!ws || mask < 1 || mask > 15) return fail(SD_ERR_INVALID, "sd_ws_set_stage_mask: mask must be in [1, 15]");
     priv(ws)->stage_mask = mask;
     return SD_OK;
 }
@@ -839,8 +804,7 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
 extern "C" int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8) {
     if (!ws || !h_out8 || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_debug_counters: bad argument");
     SD_CUDA_TRY(cudaDeviceSynchronize());
-    if (priv(ws)->organized) SD_CUDA_TRY(cudaMemcpy(h_out8, ws->ost[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
-    else SD_CUDA_TRY(cudaMemcpy(h_out8, ws->gs[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
+    SD_CUDA_TRY(cudaMemcpy(h_out8, ws->gs[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
     return SD_OK;
 }
 

@@ -79,11 +79,17 @@ __device__ __forceinline__ bool eval_pred(const PredRt& p, float x, float y, flo
 // ---------------------------------------------------------------------------------------------
 // compaction
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kCompactThreads)
+// One tile = kCompactTile consecutive points.  A thread loads kCompactItems consecutive points with
+// 128-bit loads (x, y, z and the source index), evaluates the predicate, the block scans the keep counts,
+// one warp chains the tile to its predecessors (decoupled look-back), the survivors are staged in shared
+// memory in output order and leave through fully coalesced stores.
+__global__ void __launch_bounds__(kCompactThreads, 4)
 compact_kernel(const CompactJob* __restrict__ jobs) {
     __shared__ int s_scan[33];
     __shared__ int s_tile;
     __shared__ unsigned long long s_excl;
+    __shared__ float s_x[kCompactTile], s_y[kCompactTile], s_z[kCompactTile];
+    __shared__ int s_src[kCompactTile];
 
     const CompactJob J = jobs[blockIdx.y];
     const int n = *J.n_in;
@@ -95,8 +101,9 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     const bool need_y = (P.kind == SD_PRED_PLANE) || (J.oy != nullptr) || (P.axis == 1 && P.kind <= SD_PRED_GT);
     const bool need_z = (P.kind == SD_PRED_PLANE) || (J.oz != nullptr) || (P.axis == 2 && P.kind <= SD_PRED_GT) ||
                         (P.kind == SD_PRED_SLAB);
+    const bool need_s = (J.osrc != nullptr) && (J.src != nullptr);
 
-    const bool vec_ok = ((((uintptr_t)X) | ((uintptr_t)Y) | ((uintptr_t)Z)) & 15) == 0;   // 128-bit loads need alignment
+    const bool vec_ok = ((((uintptr_t)X) | ((uintptr_t)Y) | ((uintptr_t)Z) | ((uintptr_t)J.src)) & 15) == 0;   // 128-bit loads need alignment
     while (true) {
         if (tid == 0) s_tile = (int)atomicAdd(&J.ctl->ticket, 1u);
         __syncthreads();
@@ -104,62 +111,59 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
         if (tile >= ntiles) break;
         const int base = tile * kCompactTile + tid * kCompactItems;
         float x[kCompactItems], y[kCompactItems], z[kCompactItems];
-        bool keep[kCompactItems];
-        int cnt = 0;
+        int sidx[kCompactItems];
+        unsigned keep = 0u;
         if (vec_ok && base + kCompactItems <= n) {
 #pragma unroll
             for (int q = 0; q < kCompactItems / 4; ++q) {
                 float4 a = need_x ? __ldg(reinterpret_cast<const float4*>(X + base) + q) : make_float4(0, 0, 0, 0);
                 float4 b = need_y ? __ldg(reinterpret_cast<const float4*>(Y + base) + q) : make_float4(0, 0, 0, 0);
                 float4 c = need_z ? __ldg(reinterpret_cast<const float4*>(Z + base) + q) : make_float4(0, 0, 0, 0);
+                int4 d = need_s ? __ldg(reinterpret_cast<const int4*>(J.src + base) + q)
+                                : make_int4(base + 4 * q, base + 4 * q + 1, base + 4 * q + 2, base + 4 * q + 3);
                 x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
                 y[4 * q] = b.x; y[4 * q + 1] = b.y; y[4 * q + 2] = b.z; y[4 * q + 3] = b.w;
                 z[4 * q] = c.x; z[4 * q + 1] = c.y; z[4 * q + 2] = c.z; z[4 * q + 3] = c.w;
+                sidx[4 * q] = d.x; sidx[4 * q + 1] = d.y; sidx[4 * q + 2] = d.z; sidx[4 * q + 3] = d.w;
             }
 #pragma unroll
-            for (int k = 0; k < kCompactItems; ++k) { keep[k] = eval_pred(P, x[k], y[k], z[k], base + k); cnt += keep[k]; }
+            for (int k = 0; k < kCompactItems; ++k) keep |= eval_pred(P, x[k], y[k], z[k], base + k) ? (1u << k) : 0u;
         } else {
 #pragma unroll
             for (int k = 0; k < kCompactItems; ++k) {
                 const int i = base + k;
-                keep[k] = false; x[k] = y[k] = z[k] = 0.f;
+                x[k] = y[k] = z[k] = 0.f; sidx[k] = i;
                 if (i < n) {
                     if (need_x) x[k] = __ldg(X + i);
                     if (need_y) y[k] = __ldg(Y + i);
                     if (need_z) z[k] = __ldg(Z + i);
-                    keep[k] = eval_pred(P, x[k], y[k], z[k], i);
-                    cnt += keep[k];
+                    if (need_s) sidx[k] = __ldg(J.src + i);
+                    keep |= eval_pred(P, x[k], y[k], z[k], i) ? (1u << k) : 0u;
                 }
             }
         }
         int total;
-        const int excl = block_excl_scan(cnt, s_scan, &total);
+        const int excl = block_excl_scan(__popc(keep), s_scan, &total);
         if (warp_id() == 0) {
             unsigned long long e = lookback_exclusive(J.status, tile, (unsigned long long)total);
             if (lane_id() == 0) s_excl = e;
         }
-        __syncthreads();
-        int pos = (int)s_excl + excl;
-        if (tile == ntiles - 1 && tid == 0 && J.n_out) *J.n_out = (int)s_excl + total;
+        // stage the survivors in output order (block_excl_scan ended with a barrier: s_x.. are free)
+        int lpos = excl;
 #pragma unroll
         for (int k = 0; k < kCompactItems; ++k) {
-            if (keep[k]) {
-                if (J.ox) J.ox[pos] = x[k];
-                if (J.oy) J.oy[pos] = y[k];
-                if (J.oz) J.oz[pos] = z[k];
-                const int sidx = J.src ? __ldg(J.src + base + k) : (base + k);
-                if (J.osrc) J.osrc[pos] = sidx;
-                if (J.dense_mode == 1) J.dense[sidx] = make_float4(x[k], y[k], z[k], __int_as_float(pos));
-                ++pos;
-            }
+            if (keep & (1u << k)) { s_x[lpos] = x[k]; s_y[lpos] = y[k]; s_z[lpos] = z[k]; s_src[lpos] = sidx[k]; ++lpos; }
         }
-        if (J.dense_mode == 2) {          // restore the organized buffer's all-inf invariant
-            const float inf = __int_as_float(0x7f800000);
-#pragma unroll
-            for (int k = 0; k < kCompactItems; ++k)
-                if (base + k < n) J.dense[__ldg(J.src + base + k)] = make_float4(inf, inf, inf, inf);
+        __syncthreads();
+        const int out0 = (int)s_excl;
+        if (tile == ntiles - 1 && tid == 0 && J.n_out) *J.n_out = out0 + total;
+        for (int i = tid; i < total; i += kCompactThreads) {
+            if (J.ox) J.ox[out0 + i] = s_x[i];
+            if (J.oy) J.oy[out0 + i] = s_y[i];
+            if (J.oz) J.oz[out0 + i] = s_z[i];
+            if (J.osrc) J.osrc[out0 + i] = s_src[i];
         }
-        __syncthreads();   // s_tile / s_excl are rewritten by the next iteration
+        __syncthreads();   // s_tile / s_excl / staging are rewritten by the next iteration
     }
     if (scan_finish(J.ctl, J.status, max(ntiles, 0), gridDim.x)) {
         if (tid == 0) {
@@ -343,7 +347,7 @@ int sd_launch_compact(const sd::CompactJob* d_jobs, int njobs, int cap, cudaStre
     using namespace sd;
     if (njobs <= 0) return SD_OK;
     int tiles = max(1, ceil_div(cap, kCompactTile));
-    int target = max(1, (148 * 3) / njobs);
+    int target = max(1, (148 * 4) / njobs);           // every job's CTAs are resident together (4 CTAs per SM)
     dim3 grid(min(tiles, target), njobs);
     compact_kernel<<<grid, kCompactThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();

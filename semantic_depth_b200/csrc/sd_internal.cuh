@@ -8,9 +8,9 @@ namespace sd {
 
 constexpr int kSelBits0 = 11, kSelBits1 = 11, kSelBits2 = 10;   // radix-select digit widths (32 bits)
 constexpr int kSelBins = 2048;
-constexpr int kCompactThreads = 512;
+constexpr int kCompactThreads = 256;
 constexpr int kCompactItems = 8;
-constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 4096 points per tile
+constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 2048 points per tile
 constexpr int kScanTile = 4096;                                 // cell-count scan tile
 constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job
 constexpr int kPlaneSums = 9;
@@ -75,9 +75,6 @@ struct CompactJob {
     uint32_t* frame_status;     // optional: OR `empty_bit` when the output is empty
     uint32_t empty_bit;
     int32_t max_tiles;
-    float4* dense;              // optional organized (per-pixel) copy of the cloud, indexed by src
-    int32_t dense_mode;         // 1: dense[src] = (x,y,z,bits(out index)) for kept points; 2: dense[src] = +inf for every input point
-    int32_t pad_;
 };
 
 // ---- plane fit -----------------------------------------------------------------------------------------
@@ -124,8 +121,7 @@ struct GridState {
     unsigned long long acc[3][2];  // exact 128-bit fixed-point sums of avg, avg^2 (lo, hi) and the count of avg > 0
     int32_t work;                  // dynamic work counter of the search kernels (next unclaimed sorted index)
     int32_t pad_;
-    unsigned long long dbg[8];     // developer counters (cumulative): 0 k-NN queries, 1 slow-path queries, 2 list overflows,
-                                   // 3 list underflows, 4 sum of list lengths, 5 phase-1 candidates, 6 phase-2 candidates, 7 phase-2 rows
+    unsigned long long dbg[8];     // developer counters (see sd_ws_debug_counters)
 };
 struct KnnJob {
     const float* x; const float* y; const float* z; const int32_t* n;
@@ -135,7 +131,6 @@ struct KnnJob {
     int32_t* cell_of;           // [cap] level-0 cell of each point (input order)
     float4* sp;                 // [kLevels * cap] cell-sorted copies (x, y, z, bits(original index)), level L at [L*n, (L+1)*n)
     double* avg;                // [cap] mean kNN distance, by ORIGINAL index
-    double* savg;               // [cap] same, by sorted index
     int32_t* cnt;               // [cap] radius counts, by original index
     unsigned long long* scan_status; ScanCtl* scan_ctl;
     double* stats;              // mean, std, thr
@@ -148,37 +143,9 @@ struct KnnJob {
     int32_t use_sor;            // 0: every point is alive for the radius count
     int32_t count_cap;          // saturate radius counts at count_cap + 1 (-1: exact counts)
     int32_t pad_;
-    double* part;               // [kKnnMaxBlocks][3] per-CTA partial sums of the cloud statistics
     double cell_scale;          // cell edge = cell_scale * sqrt(area / n)
 };
 constexpr int kKnnMaxBlocks = 148 * 16;
-
-// ---- organized (per-pixel) neighbour search of the fused path ---------------------------------------------------
-struct OrgState {
-    unsigned long long acc[3][2];   // exact fixed-point sums of avg, avg^2 and the count of avg > 0
-    uint32_t ticket;
-    int32_t qn_knn;                 // hard k-NN queries queued
-    int32_t qn_ror;                 // hard radius queries queued
-    int32_t pad_;
-    unsigned long long dbg[8];      // cumulative: 0 knn queries, 1 knn hard, 2 fail window cert, 3 fail ray bound,
-                                    //             4 list overflow, 5 ror queries, 6 ror hard, 7 sum of list counts
-};
-struct OrgJob {
-    const float* x; const float* y; const float* z; const int32_t* src; const int32_t* n;   // compact cloud (plane-filtered)
-    float4* dense;                  // [H*W] (x,y,z,bits(index)); +inf where no point
-    OrgState* st;
-    double* avg;                    // [cap] mean k-NN distance by compact index
-    int32_t* cnt;                   // [cap] radius counts by compact index (saturated at nb_points+1)
-    int32_t* queue_knn; int32_t* queue_ror;   // [cap] compact indices of the hard queries
-    float* queue_bound;             // [cap] per queued k-NN query: an upper bound of its k-th squared distance (inf: none)
-    double* stats;                  // mean, std, thr
-    int32_t* n_alive;
-    int32_t height, width;
-    float q03, q13, q23;            // ray of pixel (u,v): (u + q03, q13 - v, q23)
-    int32_t k;
-    double std_ratio, radius;
-    int32_t nb_points, use_sor;
-};
 
 // ---- RANSAC ----------------------------------------------------------------------------------------------
 struct RansacJob {
@@ -268,8 +235,7 @@ struct SdWorkspace {
     sd::GridState* gs;                   // [F]
     int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
     float4* sp;
-    double* avg; double* savg; int32_t* cnt; double* knn_part;
-    float4* dense; sd::OrgState* ost; int32_t* queue_knn; int32_t* queue_ror;   // organized search (fused path)
+    double* avg; int32_t* cnt;
     unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
     // ransac per (frame, chain 0..2)
     double* hyp_coeff; int32_t* hyp_counts; double* best_coeff;
@@ -293,10 +259,6 @@ int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStrea
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
 int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
-int sd_launch_org_fill(float4* dense, size_t count, cudaStream_t st);
-int sd_launch_org_knn(const sd::OrgJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
-int sd_launch_org_apply_sor(const sd::OrgJob* d_jobs, int njobs, int cap, cudaStream_t st);
-int sd_launch_org_ror(const sd::OrgJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
 int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,

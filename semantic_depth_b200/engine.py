@@ -206,8 +206,9 @@ class FusionEngine:
         """Record CUDA events around the pixel-stage kernel and the whole fused call (see sd_fusion.h)."""
         check(self.lib.sd_ws_enable_timing(self._ws, int(enable)), "sd_ws_enable_timing")
 
-    def set_stage_mask(self, mask: int = 3):
-        """1 = pixel stage only, 2 = cloud stages + answers only, 3 = the whole path (default)."""
+    def set_stage_mask(self, mask: int = 15):
+        """Bit 0 = pixel stage, bit 1 = cloud stages up to the search grid + fence chain, bit 2 = the k-NN
+        kernel, bit 3 = radius search .. answers; 15 = the whole path (default)."""
         check(self.lib.sd_ws_set_stage_mask(self._ws, int(mask)), "sd_ws_set_stage_mask")
 
     def stage_ms(self, which: str = "pixel") -> float:
@@ -218,7 +219,7 @@ class FusionEngine:
     def debug_counters(self, frame: int = 0) -> dict:
         out = (C.c_ulonglong * 8)()
         check(self.lib.sd_ws_debug_counters(self._ws, frame, out), "sd_ws_debug_counters")
-        names = ("knn_queries", "knn_hard", "fail_window", "fail_ray_bound", "list_overflow", "unused", "ror_hard", "list_sum")
+        names = tuple(f"c{i}" for i in range(8))
         return {n: int(v) for n, v in zip(names, out)}
 
     def final_cloud(self, frame: int, which: str = "road"):

@@ -69,7 +69,7 @@ class _Slot:
         self.engine = FusionEngine(height, width, max_frames=batch, max_hypotheses=max_hyp, device=device)
         self.stream = torch.cuda.Stream(device=device)
         self.done = torch.cuda.Event()
-        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         self.graphs = {}           # key -> CUDAGraph
         self.stage_logits = None   # device staging for host inputs
         self.stage_disp = None
@@ -95,8 +95,9 @@ class FramePipeline:
         self.use_graphs = use_graphs
         self.slots = [_Slot(height, width, batch, self.device) for _ in range(slots)]
         self.timing = timing
-        self.pixel_ms: list[float] = []
-        self.total_ms: list[float] = []
+        self.pixel_ms: list[float] = []     # pixel stage (3 kernels)
+        self.knn_ms: list[float] = []       # the k-NN kernel of the statistical filter
+        self.total_ms: list[float] = []     # first to last kernel of the batch
         self._next = 0
 
     # -- internals ---------------------------------------------------------------------------------
@@ -106,7 +107,8 @@ class FramePipeline:
         slot.done.synchronize()
         if self.timing:
             self.pixel_ms.append(slot.ev[0].elapsed_time(slot.ev[1]))
-            self.total_ms.append(slot.ev[0].elapsed_time(slot.ev[2]))
+            self.knn_ms.append(slot.ev[2].elapsed_time(slot.ev[3]))
+            self.total_ms.append(slot.ev[0].elapsed_time(slot.ev[4]))
         raw = np.frombuffer(slot.host_results[: slot.nbytes].numpy().tobytes(), dtype=RESULT_DTYPE).copy()
         slot.busy = False
         return slot.tag, FusionResult(raw)
@@ -117,12 +119,13 @@ class FramePipeline:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=slot.stream):
             eng.enqueue(logits, disp, intr, self.params)
-        eng.set_stage_mask(3)
+        eng.set_stage_mask(15)
         return g
 
     def _launch(self, slot: _Slot, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, key):
-        """Enqueue one batch on the slot's stream.  With timing on, the pixel stage and the cloud stages
-        are two graphs (or two eager calls) so that torch events can bracket the pixel-stage kernel."""
+        """Enqueue one batch on the slot's stream.  With timing on, the path is split into four graphs (or four
+        eager calls) -- pixel stage | cloud stages up to the search grid | k-NN kernel | the rest -- so that
+        torch events can bracket the pixel stage and the k-NN kernel."""
         eng = slot.engine
         b = logits.shape[0]
         if self.use_graphs:
@@ -130,21 +133,22 @@ class FramePipeline:
             if g is None:
                 eng.enqueue(logits, disp, intr, self.params)          # eager once: builds the job tables
                 slot.stream.synchronize()
-                g = ((self._capture(slot, logits, disp, intr, 1), self._capture(slot, logits, disp, intr, 2))
-                     if self.timing else (self._capture(slot, logits, disp, intr, 3),))
+                g = (tuple(self._capture(slot, logits, disp, intr, m) for m in (1, 2, 4, 8))
+                     if self.timing else (self._capture(slot, logits, disp, intr, 15),))
                 slot.graphs[key] = g
             if self.timing:
-                slot.ev[0].record(slot.stream); g[0].replay(); slot.ev[1].record(slot.stream); g[1].replay()
-                slot.ev[2].record(slot.stream)
+                for k, gk in enumerate(g):
+                    slot.ev[k].record(slot.stream)
+                    gk.replay()
+                slot.ev[4].record(slot.stream)
             else:
                 g[0].replay()
         elif self.timing:
-            slot.ev[0].record(slot.stream)
-            eng.set_stage_mask(1); eng.enqueue(logits, disp, intr, self.params)
-            slot.ev[1].record(slot.stream)
-            eng.set_stage_mask(2); eng.enqueue(logits, disp, intr, self.params)
-            eng.set_stage_mask(3)
-            slot.ev[2].record(slot.stream)
+            for k, m in enumerate((1, 2, 4, 8)):
+                slot.ev[k].record(slot.stream)
+                eng.set_stage_mask(m); eng.enqueue(logits, disp, intr, self.params)
+            eng.set_stage_mask(15)
+            slot.ev[4].record(slot.stream)
         else:
             eng.enqueue(logits, disp, intr, self.params)
         slot.nbytes = b * C.sizeof(SdFrameResult)

@@ -42,7 +42,7 @@ class CpuBaseline:
 
     def __init__(self, height: int, width: int, procs: int | None = None, kd_workers: int | None = None):
         cores = os.cpu_count() or 1
-        self.procs = max(1, min(cores, 16) if procs is None else procs)
+        self.procs = max(1, min(cores, 32) if procs is None else procs)
         self.kd_workers = max(1, cores // self.procs) if kd_workers is None else kd_workers
         self.cores_used = min(cores, self.procs * self.kd_workers)
         self.height, self.width = height, width

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=3, help="batches in flight per GPU")
     ap.add_argument("--batches", type=int, default=6, help="distinct input batches resident in HBM (cycled)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-kernel-timing", action="store_true", help="one CUDA graph per batch instead of four event-bracketed segments")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 40)")
@@ -195,7 +196,7 @@ def run_b200(a):
     d_disp = [t.to(dev) for t in h_disp]
     input_bytes = nb * B * HW * 20
 
-    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=True)
+    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=not a.no_kernel_timing)
 
     def barrier():
         torch.cuda.synchronize()

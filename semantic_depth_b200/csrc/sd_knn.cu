@@ -326,7 +326,7 @@ template <int K> struct KnnCfg {
     static constexpr int feed_cap = 4 * K + 24;                           // ... ring mode
     static constexpr int list_raw = 3 * K + 10;
     static constexpr int list_cap = list_raw > 126 ? 126 : list_raw;      // phase-2 list entries per query (smem, 7-bit slots)
-    static constexpr size_t smem_bytes = ((size_t)list_cap * sizeof(int) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;
+    static constexpr size_t smem_bytes = ((size_t)(list_cap + 1) * sizeof(int) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;   // + 1 spare row
 };
 
 template <int KS>
@@ -381,7 +381,10 @@ __device__ __forceinline__ double dist2_of(const float4& p, float qx, float qy, 
 __device__ __forceinline__ double dist2_f64(const KnnJob& J, int j, float qx, float qy, float qz) {
     return dist2_of(__ldg(J.sp + j), qx, qy, qz);
 }
-constexpr int kBatch = 4;              // candidates whose loads are issued together (the loops are latency-bound)
+#ifndef SD_KNN_BATCH
+#define SD_KNN_BATCH 4
+#endif
+constexpr int kBatch = SD_KNN_BATCH;             // candidates whose loads are issued together (the loops are latency-bound)
 
 // visit the cells that square(r) adds to square(rold) (rold < 0: everything) at one level, row by row
 template <typename F>
@@ -568,16 +571,20 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 if (todo && !heavy) {
                     for (int ri = 0; ri < nruns; ++ri) {
                         const int2 se = s_seg[ri][tid];
-                        for (int j0 = se.x; j0 < se.y; j0 += kBatch) {
+                        // full batches need no bound checks; an overflowing list parks its writes in the spare row
+                        int j0 = se.x;
+                        for (; j0 + kBatch <= se.y; j0 += kBatch) {
+                            const float4* __restrict__ pc = J.sp + j0;
                             float4 c[kBatch];
 #pragma unroll
-                            for (int u = 0; u < kBatch; ++u) c[u] = __ldg(J.sp + min(j0 + u, se.y - 1));
+                            for (int u = 0; u < kBatch; ++u) c[u] = __ldg(pc + u);
 #pragma unroll
                             for (int u = 0; u < kBatch; ++u) {
-                                const bool in = (j0 + u < se.y) && key_of(c[u], qx, qy, qz) <= band;
-                                if (in && cnt < kListCap) s_list[cnt][tid] = j0 + u;
-                                cnt += in ? 1 : 0;
+                                if (key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = j0 + u; ++cnt; }
                             }
+                        }
+                        for (; j0 < se.y; ++j0) {
+                            if (key_f32(J, j0, qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = j0; ++cnt; }
                         }
                     }
                 }
@@ -805,12 +812,17 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
                     ok[u] = (u < 4) ? (j < e) : (j >= s);
                     c[u] = __ldg(J.sp + (ok[u] ? j : i));
                 }
+                unsigned amb = 0u;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const float d2f = key_of(c[u], qx, qy, qz);             // fp32 pre-test, relative error < 1.5e-6
-                    bool in = d2f < r2_in;
-                    if (!in && d2f <= r2_out) in = dist2_of(c[u], qx, qy, qz) <= r2;   // inside the error band: decide in fp64
-                    count += (ok[u] && in) ? 1 : 0;
+                    count += (ok[u] && d2f < r2_in) ? 1 : 0;
+                    amb |= (ok[u] && d2f >= r2_in && d2f <= r2_out) ? (1u << u) : 0u;
+                }
+                if (amb) {                                                  // inside the error band (rare): decide in fp64
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if ((amb >> u) & 1u) count += (dist2_of(c[u], qx, qy, qz) <= r2) ? 1 : 0;
                 }
                 jr += 4; jl -= 4;
                 done = (cap >= 0 && count > cap);

@@ -805,20 +805,32 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
             mid = min(max(mid, s), e);
             int jl = mid - 1, jr = mid;
             while (!done && (jl >= s || jr < e)) {
-                float4 c[8]; bool ok[8];
+                float4 c[8];
+                unsigned okm = 0xffu;
+                if (jr + 4 <= e && jl - 3 >= s) {                            // both sides full: no bound checks
+                    const float4* __restrict__ pr = J.sp + jr;
+                    const float4* __restrict__ pl = J.sp + (jl - 3);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int j = (u < 4) ? jr + u : jl - (u - 4);
-                    ok[u] = (u < 4) ? (j < e) : (j >= s);
-                    c[u] = __ldg(J.sp + (ok[u] ? j : i));
+                    for (int u = 0; u < 4; ++u) { c[u] = __ldg(pr + u); c[4 + u] = __ldg(pl + u); }
+                } else {
+                    okm = 0u;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int j = (u < 4) ? jr + u : jl - (u - 4);
+                        const bool ok = (u < 4) ? (j < e) : (j >= s);
+                        okm |= ok ? (1u << u) : 0u;
+                        c[u] = __ldg(J.sp + (ok ? j : i));
+                    }
                 }
-                unsigned amb = 0u;
+                unsigned inm = 0u, amb = 0u;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const float d2f = key_of(c[u], qx, qy, qz);             // fp32 pre-test, relative error < 1.5e-6
-                    count += (ok[u] && d2f < r2_in) ? 1 : 0;
-                    amb |= (ok[u] && d2f >= r2_in && d2f <= r2_out) ? (1u << u) : 0u;
+                    inm |= (d2f < r2_in) ? (1u << u) : 0u;
+                    amb |= (d2f >= r2_in && d2f <= r2_out) ? (1u << u) : 0u;
                 }
+                count += __popc(inm & okm);
+                amb &= okm;
                 if (amb) {                                                  // inside the error band (rare): decide in fp64
 #pragma unroll
                     for (int u = 0; u < 8; ++u)

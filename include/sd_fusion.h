@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SD_ABI_VERSION 1
+#define SD_ABI_VERSION 2
 
 enum {
     SD_OK = 0,
@@ -105,6 +105,8 @@ typedef struct SdParams {
     int32_t use_sor;          /* 1 */
     int32_t use_ror;          /* 1 */
     int32_t approach_both;    /* 1 = rw and f2f, 0 = rw only (:273) */
+    int32_t label_mode;       /* 0 = softmax > prob_thr (the reference, :555-556,563-564); 1 = argmax over the classes */
+    int32_t pad_;
 } SdParams;
 
 /* One frame's answers (what process_frame returns at :460 plus everything observable on the way). */
@@ -156,12 +158,27 @@ void sd_ws_destroy(SdWorkspace* ws);
  *   flat pixel index; capacity H*W each, per frame stride H*W.  d_counts [B][3] int32 =
  *   {road_gather, road_z, fence_gather}. */
 #define SD_PIX_RAW_DISPARITY 1   /* flags: d_disp[b][0] already is the blended, scaled disparity of :145 (skip blend and scale) */
+#define SD_PIX_LABEL_ARGMAX 2    /* flags: label by argmax over the three classes instead of softmax > prob_thr */
 int sd_pixel_fuse(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
                   int batch, int height, int width, const SdCamera* cam, double prob_thr, float road_z_to_meter, int flags,
                   float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
                   float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
                   int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp,
                   SdWorkspace* ws, void* stream);
+
+/* Same with the FCN-8s head left unexpanded: the logits are never materialised, the label
+ * kernel evaluates fcn8s/fcn.py:207-213 -- conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same') -- itself.
+ *   d_scores [B][H/8][W/8][3] fp32 (second_skip), d_up_weights [16][16][3 out][3 in] fp32 (TF kernel layout),
+ *   d_up_bias [3] fp32.  Arithmetic contract: fp32, no FMA, taps accumulated from 0.0 in the order (low-res row,
+ *   low-res column, input channel) ascending, bias added last.  d_logits_out (optional) [B][H*W][3] receives the
+ *   upsampled logits, i.e. the tensor the reference fetches as 'logits:0' (fcn.py:241). */
+int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_weights, const float* d_up_bias,
+                         const float* d_disp, int batch, int height, int width, const SdCamera* cam,
+                         double prob_thr, float road_z_to_meter, int flags,
+                         float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
+                         float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
+                         int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp, float* d_logits_out,
+                         SdWorkspace* ws, void* stream);
 
 /* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
 /* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
@@ -236,6 +253,13 @@ int sd_fuse_frames(const float* d_logits, const float* d_disp, int batch, int he
                    const SdCamera* cam, const SdParams* params,
                    const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
                    SdFrameResult* d_results, SdWorkspace* ws, void* stream);
+
+/* The fused path fed by the unexpanded FCN-8s head (see sd_pixel_fuse_scores): 0.19 B/pixel of scores instead of
+ * 12 B/pixel of logits. */
+int sd_fuse_frames_scores(const float* d_scores, const float* d_up_weights, const float* d_up_bias,
+                          const float* d_disp, int batch, int height, int width,
+                          const SdCamera* cam, const SdParams* params, SdFrameResult* d_results,
+                          SdWorkspace* ws, void* stream);
 
 /* Number of kernels one sd_fuse_frames call launches for these parameters (independent of batch). */
 int sd_fuse_kernel_count(const SdParams* params, int with_ransac);

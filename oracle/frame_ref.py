@@ -32,6 +32,50 @@ def labels_from_logits(logits, prob_thr=0.5):
     return p[:, 0] > prob_thr, p[:, 1] > prob_thr
 
 
+def upsample_scores(scores, weights, bias):
+    """FCN-8s' last layer (fcn8s/fcn.py:207-213): ``conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same')``.
+
+    ``scores`` [h, w, 3] fp32 (``second_skip``), ``weights`` [16, 16, 3(out), 3(in)] fp32 (TF layout
+    kh, kw, out, in), ``bias`` [3] fp32  ->  logits [8h*8w, 3] fp32, the tensor the reference fetches as
+    ``logits:0`` (fcn.py:241).  Output pixel (y, x) receives the taps ``ky = y + 4 - 8*iy`` in [0, 16): two
+    low-res rows and two low-res columns (zero outside the map), three input channels each.  TF's own
+    summation order is not reproducible; the contract is fp32, no FMA, accumulated
+    from 0.0 in the order (iy ascending, ix ascending, ci ascending), bias added last.
+    """
+    s = np.asarray(scores, dtype=np.float32)
+    w = np.asarray(weights, dtype=np.float32)
+    b = np.asarray(bias, dtype=np.float32)
+    h, wd, _ = s.shape
+    H, W = 8 * h, 8 * wd
+    y = np.arange(H); x = np.arange(W)
+    iy0 = (y + 4) // 8 - 1; ix0 = (x + 4) // 8 - 1
+    pad = np.zeros((h + 2, wd + 2, 3), dtype=np.float32)
+    pad[1:-1, 1:-1] = s
+    out = np.empty((H, W, 3), dtype=np.float32)
+    for co in range(3):
+        acc = np.zeros((H, W), dtype=np.float32)
+        for dy in range(2):
+            iy = iy0 + dy
+            ky = y + 4 - 8 * iy                      # in [0, 16)
+            for dx in range(2):
+                ix = ix0 + dx
+                kx = x + 4 - 8 * ix
+                for ci in range(3):
+                    sv = pad[iy[:, None] + 1, ix[None, :] + 1, ci]
+                    wv = w[ky[:, None], kx[None, :], co, ci]
+                    acc = acc + sv * wv               # fp32 product, fp32 sum
+        out[:, :, co] = acc + b[co]
+    return out.reshape(H * W, 3)
+
+
+def labels_argmax(logits):
+    """north_star's wording of the labelling: ``argmax`` over the three classes (first maximum wins, like
+    ``np.argmax``); road = class 0, fence = class 1.  An alternative to the reference's ``softmax > 0.5``."""
+    l = np.asarray(logits, dtype=np.float32).reshape(-1, 3)
+    a = np.argmax(l, axis=1)
+    return a == 0, a == 1
+
+
 def label_margin(logits):
     """|p_c - 0.5| of the closest class per pixel; pixels below ~1e-12 are the documented tie class."""
     l = np.asarray(logits, dtype=np.float64).reshape(-1, 3)

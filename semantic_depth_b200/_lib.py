@@ -38,6 +38,7 @@ class SdParams(C.Structure):
         ("road_plane_thr", C.c_double), ("fence_plane_thr", C.c_double), ("sor_std_ratio", C.c_double),
         ("ror_radius", C.c_double), ("slab_lo", C.c_double), ("slab_hi", C.c_double), ("depth", C.c_double),
         ("ror_nb_points", C.c_int32), ("use_sor", C.c_int32), ("use_ror", C.c_int32), ("approach_both", C.c_int32),
+        ("label_mode", C.c_int32), ("pad_", C.c_int32),
     ]
 
 
@@ -75,6 +76,9 @@ SIGNATURES = {
     "sd_ws_destroy": (None, [_P]),
     "sd_pixel_fuse": (_I, [_P, _P, _P, _P, _I, _I, _I, C.POINTER(SdCamera), C.c_double, C.c_float, _I,
                            _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sd_pixel_fuse_scores": (_I, [_P, _P, _P, _P, _I, _I, _I, C.POINTER(SdCamera), C.c_double, C.c_float, _I,
+                                  _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sd_fuse_frames_scores": (_I, [_P, _P, _P, _P, _I, _I, _I, C.POINTER(SdCamera), C.POINTER(SdParams), _P, _P, _P]),
     "sd_median_mad": (_I, [_P, _I, C.POINTER(C.c_float), _P, _P]),
     "sd_filter": (_I, [_P, _P, _P, _P, _I, C.POINTER(SdPredicate), _P, _P, _P, _P, C.POINTER(C.c_int32), _P, _P]),
     "sd_plane_fit": (_I, [_P, _P, _P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_int32), _P, _P]),
@@ -116,7 +120,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.sd_abi_version() != 1:
+    if lib.sd_abi_version() != 2:
         raise SdError("libsd_fusion.so ABI version mismatch")
     _lib = lib
     return lib

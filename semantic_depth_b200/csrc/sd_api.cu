@@ -36,7 +36,7 @@ extern "C" void sd_default_params(SdParams* p, double depth) {
     const double d = depth - 0.02;                  // semantic_depth.py:254-255
     p->slab_lo = -(d + 0.05); p->slab_hi = -(d - 0.05);   // pcl.py:283
     p->depth = depth;
-    p->ror_nb_points = 80; p->use_sor = 1; p->use_ror = 1; p->approach_both = 1;
+    p->ror_nb_points = 80; p->use_sor = 1; p->use_ror = 1; p->approach_both = 1; p->label_mode = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,22 +341,51 @@ int check_n(SdWorkspace* ws, int n) {
 
 }  // namespace
 
+static int pixel_fuse_impl(const float* d_logits, const float* d_scores, const float* d_upw, const float* d_upb,
+                           const float* d_disp, const double* d_lmask, const double* d_rmask,
+                           int batch, int height, int width, const SdCamera* cam, double prob_thr, float road_z_to_meter, int flags,
+                           float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
+                           float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
+                           int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp, float* d_logits_out,
+                           SdWorkspace* ws, void* stream) {
+    if (!ws || (!d_logits && !d_scores) || !d_disp || !cam || !d_counts) return fail(SD_ERR_INVALID, "sd_pixel_fuse: null argument");
+    if (height != ws->height || width != ws->width || batch > ws->max_frames || batch < 1)
+        return fail(SD_ERR_WORKSPACE, "sd_pixel_fuse: shape does not match the workspace");
+    if (d_scores && (height % 8 != 0 || width % 8 != 0 || !d_upw || !d_upb))
+        return fail(SD_ERR_INVALID, "sd_pixel_fuse_scores: frame size must be a multiple of 8 and weights / bias must be given");
+    if (!d_road_x || !d_road_y || !d_road_z || !d_road_src || !d_fence_x || !d_fence_y || !d_fence_z || !d_fence_src)
+        return fail(SD_ERR_INVALID, "sd_pixel_fuse: null cloud output");
+    SdCloudBuf road{d_road_x, d_road_y, d_road_z, d_road_src}, fence{d_fence_x, d_fence_y, d_fence_z, d_fence_src};
+    return sd_launch_pixel(d_logits, d_disp, d_lmask ? d_lmask : ws->lmask, d_rmask ? d_rmask : ws->rmask,
+                           batch, height, width, *cam, prob_thr, road_z_to_meter, flags & SD_PIX_RAW_DISPARITY, road, fence, height * width,
+                           d_counts + 0, d_counts + 1, d_counts + 2, 3, d_labels, d_points, d_disp_pp,
+                           ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, (cudaStream_t)stream,
+                           d_scores, d_upw, d_upb, d_logits_out, (flags & SD_PIX_LABEL_ARGMAX) ? 1 : 0);
+}
+
 extern "C" int sd_pixel_fuse(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
                              int batch, int height, int width, const SdCamera* cam, double prob_thr, float road_z_to_meter, int flags,
                              float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
                              float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
                              int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp,
                              SdWorkspace* ws, void* stream) {
-    if (!ws || !d_logits || !d_disp || !cam || !d_counts) return fail(SD_ERR_INVALID, "sd_pixel_fuse: null argument");
-    if (height != ws->height || width != ws->width || batch > ws->max_frames || batch < 1)
-        return fail(SD_ERR_WORKSPACE, "sd_pixel_fuse: shape does not match the workspace");
-    if (!d_road_x || !d_road_y || !d_road_z || !d_road_src || !d_fence_x || !d_fence_y || !d_fence_z || !d_fence_src)
-        return fail(SD_ERR_INVALID, "sd_pixel_fuse: null cloud output");
-    SdCloudBuf road{d_road_x, d_road_y, d_road_z, d_road_src}, fence{d_fence_x, d_fence_y, d_fence_z, d_fence_src};
-    return sd_launch_pixel(d_logits, d_disp, d_lmask ? d_lmask : ws->lmask, d_rmask ? d_rmask : ws->rmask,
-                           batch, height, width, *cam, prob_thr, road_z_to_meter, flags, road, fence, height * width,
-                           d_counts + 0, d_counts + 1, d_counts + 2, 3, d_labels, d_points, d_disp_pp,
-                           ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, (cudaStream_t)stream);
+    if (!d_logits) return fail(SD_ERR_INVALID, "sd_pixel_fuse: null argument");
+    return pixel_fuse_impl(d_logits, nullptr, nullptr, nullptr, d_disp, d_lmask, d_rmask, batch, height, width, cam, prob_thr,
+                           road_z_to_meter, flags, d_road_x, d_road_y, d_road_z, d_road_src, d_fence_x, d_fence_y, d_fence_z,
+                           d_fence_src, d_counts, d_labels, d_points, d_disp_pp, nullptr, ws, stream);
+}
+
+extern "C" int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_weights, const float* d_up_bias,
+                                    const float* d_disp, int batch, int height, int width, const SdCamera* cam,
+                                    double prob_thr, float road_z_to_meter, int flags,
+                                    float* d_road_x, float* d_road_y, float* d_road_z, int32_t* d_road_src,
+                                    float* d_fence_x, float* d_fence_y, float* d_fence_z, int32_t* d_fence_src,
+                                    int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp, float* d_logits_out,
+                                    SdWorkspace* ws, void* stream) {
+    if (!d_scores) return fail(SD_ERR_INVALID, "sd_pixel_fuse_scores: null argument");
+    return pixel_fuse_impl(nullptr, d_scores, d_up_weights, d_up_bias, d_disp, nullptr, nullptr, batch, height, width, cam, prob_thr,
+                           road_z_to_meter, flags, d_road_x, d_road_y, d_road_z, d_road_src, d_fence_x, d_fence_y, d_fence_z,
+                           d_fence_src, d_counts, d_labels, d_points, d_disp_pp, d_logits_out, ws, stream);
 }
 
 extern "C" int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream) {
@@ -653,11 +682,14 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
 
 }  // namespace
 
-extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int batch, int height, int width,
-                              const SdCamera* cam, const SdParams* params,
-                              const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
-                              SdFrameResult* d_results, SdWorkspace* ws, void* stream) {
-    if (!ws || !d_logits || !d_disp || !cam || !params || !d_results) return fail(SD_ERR_INVALID, "sd_fuse_frames: null argument");
+static int fuse_impl(const float* d_logits, const float* d_scores, const float* d_upw, const float* d_upb,
+                     const float* d_disp, int batch, int height, int width,
+                     const SdCamera* cam, const SdParams* params,
+                     const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
+                     SdFrameResult* d_results, SdWorkspace* ws, void* stream) {
+    if (!ws || (!d_logits && !d_scores) || !d_disp || !cam || !params || !d_results) return fail(SD_ERR_INVALID, "sd_fuse_frames: null argument");
+    if (d_scores && (height % 8 != 0 || width % 8 != 0 || !d_upw || !d_upb))
+        return fail(SD_ERR_INVALID, "sd_fuse_frames_scores: frame size must be a multiple of 8 and weights / bias must be given");
     if (height != ws->height || width != ws->width || batch < 1 || batch > ws->max_frames)
         return fail(SD_ERR_WORKSPACE, "sd_fuse_frames: shape/batch does not match the workspace");
     const bool any_hyp = d_hyp_road || d_hyp_left || d_hyp_right;
@@ -693,7 +725,8 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
     rc = !do_pixel ? SD_OK : sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
                          ws->road[0], ws->fence[0], cap,
                          &ws->fs[0].n[SD_CNT_ROAD_GATHER], &ws->fs[0].n[SD_CNT_ROAD_Z], &ws->fs[0].n[SD_CNT_FENCE_GATHER], cnt_stride,
-                         nullptr, nullptr, nullptr, ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, st);
+                         nullptr, nullptr, nullptr, ws->pflags, ws->ptcounts, ws->ptoffs, ws->pix_tiles, st,
+                         d_scores, d_upw, d_upb, nullptr, P.label_mode);
     if (rc) return rc;
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[1], st));
     if (!do_pre && !do_knn && !do_post) return SD_OK;
@@ -748,6 +781,24 @@ extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int ba
 #undef SD_RUN
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[2], st));
     return SD_OK;
+}
+
+extern "C" int sd_fuse_frames(const float* d_logits, const float* d_disp, int batch, int height, int width,
+                              const SdCamera* cam, const SdParams* params,
+                              const int32_t* d_hyp_road, const int32_t* d_hyp_left, const int32_t* d_hyp_right, int n_hyp,
+                              SdFrameResult* d_results, SdWorkspace* ws, void* stream) {
+    if (!d_logits) return fail(SD_ERR_INVALID, "sd_fuse_frames: null argument");
+    return fuse_impl(d_logits, nullptr, nullptr, nullptr, d_disp, batch, height, width, cam, params, d_hyp_road, d_hyp_left,
+                     d_hyp_right, n_hyp, d_results, ws, stream);
+}
+
+extern "C" int sd_fuse_frames_scores(const float* d_scores, const float* d_up_weights, const float* d_up_bias,
+                                     const float* d_disp, int batch, int height, int width,
+                                     const SdCamera* cam, const SdParams* params, SdFrameResult* d_results,
+                                     SdWorkspace* ws, void* stream) {
+    if (!d_scores) return fail(SD_ERR_INVALID, "sd_fuse_frames_scores: null argument");
+    return fuse_impl(nullptr, d_scores, d_up_weights, d_up_bias, d_disp, batch, height, width, cam, params, nullptr, nullptr,
+                     nullptr, 0, d_results, ws, stream);
 }
 
 extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {

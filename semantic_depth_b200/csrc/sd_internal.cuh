@@ -266,4 +266,6 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
                     SdCloudBuf road, SdCloudBuf fence, int cap_stride,
                     int32_t* d_cnt_road_gather, int32_t* d_cnt_road_z, int32_t* d_cnt_fence, int cnt_stride,
                     uint8_t* d_labels, float* d_points, float* d_disp_pp,
-                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st);
+                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st,
+                    const float* d_scores = nullptr, const float* d_upw = nullptr, const float* d_upb = nullptr,
+                    float* d_logits_out = nullptr, int label_mode = 0);

@@ -7,6 +7,9 @@
 //   gather      points3D[road_mask] / [fence_mask]      semantic_depth.py:183-187  (raster order)
 //   z cut       remove_from_to(road, 2, 0, 7)           semantic_depth.py:206, pcl.py:35-37
 //
+//   upsample    (optional) conv2d_transpose(second_skip, 16x16, stride 8)   fcn8s/fcn.py:207-213
+//               the FCN-8s head evaluated inside the label kernel: 12 B/pixel of logits never exist
+//
 // HBM-bound: 20 B/pixel in (12 B logits + 2 x 4 B disparity), 16 B per surviving point out.
 // Three streaming kernels without any dependency between CTAs:
 //   pixel_label_kernel    a CTA owns 1024 consecutive pixels; its logits (12 KB, AoS) arrive in shared
@@ -78,6 +81,14 @@ __device__ __forceinline__ float div_to_f32(double num, double rden, double den)
     return (float)q;
 }
 
+// north_star's alternative labelling: np.argmax over the three classes (first maximum wins; NaN wins like NumPy)
+__device__ __forceinline__ int classify_argmax(float l0, float l1, float l2) {
+    int a = 0; float m = l0;
+    if (!(m != m) && (l1 > m || l1 != l1)) { a = 1; m = l1; }
+    if (!(m != m) && (l2 > m || l2 != l2)) { a = 2; }
+    return a == 0 ? 1 : (a == 1 ? 2 : 0);
+}
+
 struct PixArgs {
     const float* logits; const float* disp; const double* lmask; const double* rmask;
     int height, width, hw;
@@ -90,6 +101,12 @@ struct PixArgs {
     int32_t* tcounts;          // [B][tiles][4] per-tile counts: road (all), road kept, fence, -
     int32_t* toffs;            // [B][tiles][2] exclusive offsets of the tile's road / fence points
     int pix_tiles;
+    // score-map mode: logits = conv2d_transpose(scores, upw, 16x16, stride 8, 'same') + upb
+    const float* scores;       // [B][H/8][W/8][3] or nullptr
+    const float* upw;          // [16][16][3 out][3 in]
+    const float* upb;          // [3]
+    float* logits_out;         // optional [B][hw][3]: the upsampled logits (parity tests)
+    int label_mode;            // 0: softmax > thr (reference), 1: argmax (north_star wording)
 };
 
 // blended + scaled disparity of one pixel (semantic_depth.py:660-664,676 and :145)
@@ -123,10 +140,14 @@ pixel_label_kernel(const __grid_constant__ PixArgs a) {
     __shared__ __align__(128) float s_logits[kPixTile * 3];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_cnt[kPixThreads / 32][3];
+    __shared__ float s_upw[16 * 16 * 9];
     const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const int pix0 = tile * kPixTile;
     const int npix = min(kPixTile, a.hw - pix0);
-    if (tid == 0) {
+    const bool from_scores = a.scores != nullptr;
+    if (from_scores) {
+        for (int i = tid; i < 16 * 16 * 9; i += kPixThreads) s_upw[i] = __ldg(a.upw + i);
+    } else if (tid == 0) {
         mbar_init(&s_bar, 1);
         const uint32_t bytes = (uint32_t)npix * 12u;
         mbar_expect_tx(&s_bar, bytes);
@@ -138,7 +159,47 @@ pixel_label_kernel(const __grid_constant__ PixArgs a) {
     float l4[4] = {0.f, 0.f, 0.f, 0.f}, r4[4] = {0.f, 0.f, 0.f, 0.f};
     int v = 0, u0 = 0;
     if (active) { v = p / a.width; u0 = p - v * a.width; load_disp4(a, f, p, v, u0, l4, r4); }
-    mbar_wait(&s_bar, 0);
+    if (!from_scores) {
+        mbar_wait(&s_bar, 0);
+    } else if (active) {
+        // logits of this thread's 4 pixels: taps ky = y + 4 - 8*iy over two low-res rows / columns, fp32, no FMA,
+        // accumulated from 0.0 in the order (iy, ix, ci) ascending, bias last -- the oracle's order
+        const int sh = a.height >> 3, sw = a.width >> 3;
+        const float* sc = a.scores + (size_t)f * sh * sw * 3;
+        const int iy0 = ((v + 4) >> 3) - 1;
+        const float b0 = __ldg(a.upb), b1 = __ldg(a.upb + 1), b2 = __ldg(a.upb + 2);
+#pragma unroll
+        for (int j = 0; j < kPixPer; ++j) {
+            const int x = u0 + j;
+            const int ix0 = ((x + 4) >> 3) - 1;
+            float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const int iy = iy0 + dy, ky = v + 4 - 8 * iy;
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int ix = ix0 + dx, kx = x + 4 - 8 * ix;
+                    const bool inside = iy >= 0 && iy < sh && ix >= 0 && ix < sw;
+                    const float* sp = sc + ((size_t)(inside ? iy : 0) * sw + (inside ? ix : 0)) * 3;
+                    const float* wp = s_upw + (ky * 16 + kx) * 9;
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float sv = inside ? __ldg(sp + ci) : 0.f;
+                        acc0 = acc0 + sv * wp[0 * 3 + ci];
+                        acc1 = acc1 + sv * wp[1 * 3 + ci];
+                        acc2 = acc2 + sv * wp[2 * 3 + ci];
+                    }
+                }
+            }
+            float* lg = s_logits + (tid * kPixPer + j) * 3;
+            lg[0] = acc0 + b0; lg[1] = acc1 + b1; lg[2] = acc2 + b2;
+        }
+        if (a.logits_out) {
+            const float4* src = reinterpret_cast<const float4*>(s_logits + tid * kPixPer * 3);
+            float4* dst = reinterpret_cast<float4*>(a.logits_out + ((size_t)f * a.hw + p) * 3);
+            dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+        }
+    }
     const double q2 = (double)a.q23, q3 = (double)a.q32;
     const float thr32 = (float)a.thr;
     int n_road = 0, n_roadz = 0, n_fence = 0;
@@ -147,7 +208,7 @@ pixel_label_kernel(const __grid_constant__ PixArgs a) {
 #pragma unroll
         for (int j = 0; j < kPixPer; ++j) {
             const float* lg = s_logits + (tid * kPixPer + j) * 3;
-            int lab = classify(lg[0], lg[1], lg[2], a.thr, thr32);
+            int lab = a.label_mode ? classify_argmax(lg[0], lg[1], lg[2]) : classify(lg[0], lg[1], lg[2], a.thr, thr32);
             if (lab & 1) {
                 float dpp;
                 const float d = blend_px(a, l4[j], r4[j], u0 + j, dpp);
@@ -272,9 +333,12 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
                     SdCloudBuf road, SdCloudBuf fence, int cap_stride,
                     int32_t* d_cnt_road_gather, int32_t* d_cnt_road_z, int32_t* d_cnt_fence, int cnt_stride,
                     uint8_t* d_labels, float* d_points, float* d_disp_pp,
-                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st) {
+                    uint8_t* d_flags, int32_t* d_tcounts, int32_t* d_toffs, int pix_tiles, cudaStream_t st,
+                    const float* d_scores, const float* d_upw, const float* d_upb, float* d_logits_out, int label_mode) {
     using namespace sd;
     if (width % 4 != 0 || width < 4 || height < 1 || batch < 1) return SD_ERR_INVALID;
+    if (d_scores && (width % 8 != 0 || height % 8 != 0 || !d_upw || !d_upb)) return SD_ERR_INVALID;
+    if (!d_scores && !d_logits) return SD_ERR_INVALID;
     PixArgs a;
     a.logits = d_logits; a.disp = d_disp; a.lmask = d_lmask; a.rmask = d_rmask;
     a.height = height; a.width = width; a.hw = height * width;
@@ -285,6 +349,7 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
     a.cnt_stride = cnt_stride;
     a.labels = d_labels; a.points = d_points; a.disp_pp = d_disp_pp;
     a.flags = d_flags; a.tcounts = d_tcounts; a.toffs = d_toffs; a.pix_tiles = pix_tiles;
+    a.scores = d_scores; a.upw = d_upw; a.upb = d_upb; a.logits_out = d_logits_out; a.label_mode = label_mode;
     dim3 grid(pix_tiles, batch);
     pixel_label_kernel<<<grid, kPixThreads, 0, st>>>(a);
     pixel_scan_kernel<<<batch, 1024, 0, st>>>(a);

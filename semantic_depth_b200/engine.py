@@ -50,6 +50,9 @@ def params_struct(p: FusionParams) -> SdParams:
     s.ror_nb_points = p.ror_nb_points
     s.use_sor, s.use_ror = int(p.use_sor), int(p.use_ror)
     s.approach_both = int(p.approach == "both")
+    if p.label_mode not in ("softmax", "argmax"):
+        raise ValueError("label_mode must be 'softmax' or 'argmax'")
+    s.label_mode = int(p.label_mode == "argmax")
     return s
 
 
@@ -248,9 +251,17 @@ class FusionEngine:
     # ------------------------------------------------------------------------------------------
     # pixel stage alone
     # ------------------------------------------------------------------------------------------
-    def pixel_stage(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, prob_thr: float = 0.5,
-                    road_z_to_meter: float = 7.0, want_dense: bool = True, raw_disparity: bool = False) -> dict:
-        b = self._check_inputs(logits, disp)
+    def pixel_stage(self, logits: torch.Tensor | None, disp: torch.Tensor, intr: Intrinsics, prob_thr: float = 0.5,
+                    road_z_to_meter: float = 7.0, want_dense: bool = True, raw_disparity: bool = False,
+                    scores: tuple | None = None, argmax: bool = False) -> dict:
+        """Pixel stage alone.  ``scores`` = (scores [B,H/8,W/8,3], weights [16,16,3,3], bias [3]) selects the
+        score-map mode (FCN-8s head evaluated in the kernel; ``logits`` is ignored and the upsampled logits are
+        returned as ``out['logits']``)."""
+        if scores is not None:
+            sc, upw, upb = (t.contiguous() for t in scores)
+            b = self._check_scores(sc, upw, upb, disp)
+        else:
+            b = self._check_inputs(logits, disp)
         dev, hw = self.device, self.hw
         f32 = dict(dtype=torch.float32, device=dev)
         out = {k: torch.empty((b, hw), **f32) for k in ("road_x", "road_y", "road_z", "fence_x", "fence_y", "fence_z")}
@@ -261,16 +272,54 @@ class FusionEngine:
         points = torch.empty((b, hw, 3), **f32) if want_dense else None
         disp_pp = torch.empty((b, hw), **f32) if want_dense else None
         cam = camera_struct(intr)
+        flags = (1 if raw_disparity else 0) | (2 if argmax else 0)
+        clouds = (_ptr(out["road_x"]), _ptr(out["road_y"]), _ptr(out["road_z"]), _ptr(out["road_src"]),
+                  _ptr(out["fence_x"]), _ptr(out["fence_y"]), _ptr(out["fence_z"]), _ptr(out["fence_src"]))
+        logits_out = None
         with torch.cuda.device(dev):
-            check(self.lib.sd_pixel_fuse(_ptr(logits), _ptr(disp), None, None, b, self.height, self.width, C.byref(cam),
-                                         prob_thr, road_z_to_meter, 1 if raw_disparity else 0,
-                                         _ptr(out["road_x"]), _ptr(out["road_y"]), _ptr(out["road_z"]), _ptr(out["road_src"]),
-                                         _ptr(out["fence_x"]), _ptr(out["fence_y"]), _ptr(out["fence_z"]), _ptr(out["fence_src"]),
-                                         _ptr(counts), _ptr(labels), _ptr(points), _ptr(disp_pp), self._ws, _stream_ptr()),
-                  "sd_pixel_fuse")
+            if scores is not None:
+                logits_out = torch.empty((b, hw, 3), **f32) if want_dense else None
+                check(self.lib.sd_pixel_fuse_scores(_ptr(sc), _ptr(upw), _ptr(upb), _ptr(disp), b, self.height, self.width,
+                                                    C.byref(cam), prob_thr, road_z_to_meter, flags, *clouds,
+                                                    _ptr(counts), _ptr(labels), _ptr(points), _ptr(disp_pp), _ptr(logits_out),
+                                                    self._ws, _stream_ptr()), "sd_pixel_fuse_scores")
+            else:
+                check(self.lib.sd_pixel_fuse(_ptr(logits), _ptr(disp), None, None, b, self.height, self.width, C.byref(cam),
+                                             prob_thr, road_z_to_meter, flags, *clouds,
+                                             _ptr(counts), _ptr(labels), _ptr(points), _ptr(disp_pp), self._ws, _stream_ptr()),
+                      "sd_pixel_fuse")
             torch.cuda.current_stream().synchronize()
-        out.update(counts=counts.cpu().numpy(), labels=labels, points=points, disp_pp=disp_pp)
+        out.update(counts=counts.cpu().numpy(), labels=labels, points=points, disp_pp=disp_pp, logits=logits_out)
         return out
+
+    def _check_scores(self, sc, upw, upb, disp) -> int:
+        for t in (sc, upw, upb, disp):
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise TypeError("score-map mode needs contiguous CUDA float32 tensors")
+        if self.height % 8 or self.width % 8:
+            raise ValueError("score-map mode needs frame sizes that are multiples of 8")
+        b = disp.shape[0]
+        if tuple(disp.shape) != (b, 2, self.height, self.width) or tuple(sc.shape) != (b, self.height // 8, self.width // 8, 3):
+            raise ValueError(f"expected disp [B,2,{self.height},{self.width}] and scores [B,{self.height // 8},{self.width // 8},3]")
+        if tuple(upw.shape) != (16, 16, 3, 3) or tuple(upb.shape) != (3,):
+            raise ValueError("expected up-sampling weights [16,16,3,3] (kh, kw, out, in) and bias [3]")
+        if b < 1 or b > self.max_frames:
+            raise ValueError(f"batch {b} exceeds the engine's max_frames={self.max_frames}")
+        return b
+
+    def fuse_frames_scores(self, scores: torch.Tensor, weights: torch.Tensor, bias: torch.Tensor, disp: torch.Tensor,
+                           intr: Intrinsics, params: FusionParams | None = None) -> FusionResult:
+        """The fused path fed by the unexpanded FCN-8s head (``second_skip`` scores + the transposed-conv kernel of
+        fcn8s/fcn.py:207-213): the 12 B/pixel logits tensor is never materialised."""
+        params = params or FusionParams()
+        sc, upw, upb = scores.contiguous(), weights.contiguous(), bias.contiguous()
+        b = self._check_scores(sc, upw, upb, disp)
+        cam, ps = camera_struct(intr), params_struct(params)
+        with torch.cuda.device(self.device):
+            check(self.lib.sd_fuse_frames_scores(_ptr(sc), _ptr(upw), _ptr(upb), _ptr(disp), b, self.height, self.width,
+                                                 C.byref(cam), C.byref(ps), _ptr(self._results), self._ws, _stream_ptr()),
+                  "sd_fuse_frames_scores")
+            return self.fetch(b)
 
     # ------------------------------------------------------------------------------------------
     # per-call cloud ops (SoA device tensors in, device tensors / host scalars out)

@@ -49,6 +49,17 @@ def labels_from_logits(logits, shape, prob_thr: float = 0.5):
     return _back((lab & 1) != 0, was_torch), _back((lab & 2) != 0, was_torch)
 
 
+def upsample_scores(scores, weights, bias):
+    """FCN-8s' last layer, ``conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same')`` (fcn8s/fcn.py:207-213):
+    scores [h,w,3] -> logits [8h*8w, 3] fp32, evaluated by the label kernel (fp32, fixed summation order)."""
+    sc, was_torch = _dev(scores)
+    h, w = sc.shape[0] * 8, sc.shape[1] * 8
+    eng = frame_engine(h, w)
+    disp = torch.ones((1, 2, h, w), dtype=torch.float32, device=sc.device)
+    out = eng.pixel_stage(None, disp, Intrinsics.synthetic(w), scores=(sc.reshape(1, h // 8, w // 8, 3), _dev(weights)[0], _dev(bias)[0]))
+    return _back(out["logits"].reshape(h * w, 3), was_torch)
+
+
 def post_process_disparity(disp):
     """DepthFrame.post_processing + the fp32 cast (semantic_depth.py:656-664,676): [2,H,W] -> [H,W]."""
     d, was_torch = _dev(disp)
@@ -69,6 +80,15 @@ def reproject_to_3d(disparity, intr: Intrinsics):
     pair = torch.stack([d, d], dim=0).reshape(1, 2, h, w).contiguous()
     out = eng.pixel_stage(lg, pair, intr, raw_disparity=True)
     return _back(out["points"].reshape(h, w, 3), was_torch)
+
+
+def fuse_frames_from_scores(scores, weights, bias, disp, intrinsics: Intrinsics, params: FusionParams | None = None):
+    """``fuse_frames`` fed by the unexpanded FCN-8s head: ``scores`` [B,H/8,W/8,3] (``second_skip``), ``weights``
+    [16,16,3,3] and ``bias`` [3] of the last transposed convolution (fcn8s/fcn.py:207-213), ``disp`` [B,2,H,W]."""
+    b, _, h, w = disp.shape
+    sc, _ = _dev(scores)
+    eng = frame_engine(h, w, max_frames=b, device=sc.device)
+    return eng.fuse_frames_scores(sc, _dev(weights)[0], _dev(bias)[0], _dev(disp)[0], intrinsics, params)
 
 
 def fuse_frames(logits, disp, intrinsics: Intrinsics, params: FusionParams | None = None, ransac_hypotheses=None):

@@ -84,6 +84,7 @@ class FusionParams:
     fence_plane_thr: float = 1.0        # :294-298, 305-309
     # labels -----------------------------------------------------------------------------------
     prob_thr: float = 0.5               # softmax > 0.5                            :555-556,563-564
+    label_mode: str = "softmax"         # "softmax" (the reference) | "argmax" (north_star's wording of the labelling)
 
     def slab_bounds(self) -> tuple[float, float]:
         """(lo, hi) with lo < z < hi, computed exactly as the reference's Python doubles do.

@@ -75,6 +75,35 @@ def make_frame(height: int, width: int, seed: int = 0, intr: Intrinsics | None =
     return np.ascontiguousarray(logits), np.ascontiguousarray(disp), intr
 
 
+def make_frame_scores(height: int, width: int, seed: int = 0, intr: Intrinsics | None = None):
+    """The same scene with the FCN-8s head left unexpanded: (scores [H/8, W/8, 3], weights [16,16,3,3],
+    bias [3], disp [2,H,W], intrinsics).  Scores are the scene labels at 1/8 resolution plus N(0,1) noise;
+    the transposed-conv kernel is a bilinear interpolation kernel per class plus the reference's
+    truncated-normal(0.01) initialisation noise (fcn8s/fcn.py:161,207-213)."""
+    if height % 8 or width % 8:
+        raise ValueError("the score-map mode needs frame sizes that are multiples of 8")
+    intr = intr or Intrinsics.synthetic(width)
+    label, depth = scene_geometry(height, width, intr)
+    rng = np.random.default_rng(seed)
+    h, w = height // 8, width // 8
+    low = label[4::8, 4::8]
+    scores = rng.standard_normal((h, w, 3), dtype=np.float32)
+    scores[np.arange(h)[:, None], np.arange(w)[None, :], low] += np.float32(LOGIT_MARGIN)
+    k = np.arange(16, dtype=np.float64)
+    tri = 1.0 - np.abs(k - 7.5) / 8.0                         # bilinear kernel of a stride-8 upsample
+    weights = np.zeros((16, 16, 3, 3), dtype=np.float32)
+    for c in range(3):
+        weights[:, :, c, c] = np.outer(tri, tri).astype(np.float32)
+    weights += np.clip(rng.standard_normal((16, 16, 3, 3)), -2, 2).astype(np.float32) * np.float32(0.01)
+    bias = (rng.standard_normal(3) * 0.01).astype(np.float32)
+    eps = rng.standard_normal((height, width), dtype=np.float32)
+    scene_disp = (intr.f * intr.b / depth / width).astype(np.float32)
+    left = scene_disp * (np.float32(1.0) + np.float32(DISP_NOISE) * eps)
+    right = np.ascontiguousarray(left[:, ::-1]) * np.float32(FLIP_GAIN)
+    disp = np.stack([left, right], axis=0).astype(np.float32)
+    return np.ascontiguousarray(scores), weights, bias, np.ascontiguousarray(disp), intr
+
+
 def make_batch(n_frames: int, height: int, width: int, first_seed: int = 0,
                intr: Intrinsics | None = None):
     """Batch of frames: logits [B,H*W,3], disp [B,2,H,W]; frame i uses seed first_seed+i."""

@@ -10,6 +10,8 @@ and the reference lines each function follows.  Additive entry points cover what
 * ``post_process_disparity``  -- DepthFrame.post_processing + cast, semantic_depth.py:656-664,676
 * ``reproject_to_3d``         -- DepthFrame.compute_3D_points (cv2.reprojectImageTo3D), :686-697
 * ``fuse_frames``             -- the whole fusion section of process_frame, :183-324, batched
+* ``upsample_scores`` / ``fuse_frames_from_scores`` -- the same path fed by FCN-8s' unexpanded head
+  (``second_skip`` + the last transposed convolution, fcn8s/fcn.py:207-213)
 """
 from semantic_depth_b200.pcl_gpu import (  # noqa: F401
     remove_from_to, remove_noise_by_mad, mad, remove_noise_by_fitting_plane,
@@ -18,5 +20,5 @@ from semantic_depth_b200.pcl_gpu import (  # noqa: F401
     statistical_outlier_removal, radius_outlier_removal,
 )
 from semantic_depth_b200.frame_ops import (  # noqa: F401
-    labels_from_logits, post_process_disparity, reproject_to_3d, fuse_frames,
+    labels_from_logits, post_process_disparity, reproject_to_3d, fuse_frames, upsample_scores, fuse_frames_from_scores,
 )

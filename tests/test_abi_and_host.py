@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in sd_fusion.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes prototype"
-    assert lib.sd_abi_version() == 1
+    assert lib.sd_abi_version() == 2
 
 
 def test_struct_layouts_and_defaults(lib):

@@ -110,3 +110,29 @@ def test_sor_ror_oracle_small():
     assert avg.shape == (3000,) and np.all(avg > 0) and thr == mu + 0.5 * sd and 0 < keep.size < 3000
     cnt = frame_ref.radius_counts(pts, 0.5)
     assert cnt.min() >= 1 and np.array_equal(frame_ref.keep_radius_outlier_removal(pts, 80, 0.5), np.flatnonzero(cnt > 80))
+
+
+def test_upsample_oracle_matches_scatter_formulation():
+    """the gather form of the 16x16 / stride-8 transposed convolution (what the kernel evaluates)
+    against the textbook scatter form in fp64."""
+    from semantic_depth_b200 import scene
+    sc, w, b, disp, intr = scene.make_frame_scores(64, 128, 3)
+    lg = frame_ref.upsample_scores(sc, w, b)
+    h, wd, _ = sc.shape
+    ref = np.zeros((8 * h + 16, 8 * wd + 16, 3))
+    for iy in range(h):
+        for ix in range(wd):
+            ref[8 * iy:8 * iy + 16, 8 * ix:8 * ix + 16, :] += np.einsum("c,yxoc->yxo", sc[iy, ix].astype(np.float64), w.astype(np.float64))
+    ref = ref[4:4 + 8 * h, 4:4 + 8 * wd] + b
+    assert lg.dtype == np.float32 and lg.shape == (64 * 128, 3)
+    assert np.abs(ref.reshape(-1, 3) - lg).max() < 1e-5
+    # the scene stays usable in this mode: both classes present and the fused oracle answers
+    o = frame_ref.fuse_frame(lg, disp, intr.as_q32(), intr.disparity_mult)
+    assert o["counts"]["road_gather"] > 500 and o["counts"]["fence_gather"] > 500
+
+
+def test_argmax_labels_oracle():
+    lg = np.float32([[1, 0, 0], [0, 1, 0], [0, 0, 1], [2, 2, 1], [0, 3, 3], [np.nan, 1, 0]])
+    road, fence = frame_ref.labels_argmax(lg)
+    assert road.tolist() == [True, False, False, True, False, True]      # first maximum wins; NaN wins like np.argmax
+    assert fence.tolist() == [False, True, False, False, True, False]

@@ -274,6 +274,42 @@ def run_b200(a):
         mismatches += bad
         e2e = (ke, e2e_ms)
 
+    # ---- the same end-to-end call in the score-map mode: FCN-8s' head is evaluated inside the
+    #      label kernel, so 0.19 B/pixel of scores cross PCIe instead of 12 B/pixel of logits
+    e2e_sc = None
+    if not a.skip_e2e and H % 8 == 0 and W % 8 == 0:
+        ke = a.e2e_steps or min(a.steps, 40)
+        nsb = min(nb, 3)
+        h_scores = [torch.empty((B, H // 8, W // 8, 3), dtype=torch.float32).pin_memory() for _ in range(nsb)]
+        upw = upb = None
+        for i in range(nsb):
+            for f in range(B):
+                sc, wts, bs, _, _ = scene.make_frame_scores(H, W, seed=rank * 100000 + i * B + f, intr=intr)
+                h_scores[i][f].copy_(torch.from_numpy(sc))
+            upw, upb = torch.from_numpy(wts).to(dev), torch.from_numpy(bs).to(dev)
+        for i in range(max(3, len(pipe.slots))):
+            pipe.submit_host_scores(h_scores[i % nsb], upw, upb, h_disp[i % nsb], intr, tag=i % nsb)
+        first = {t: r.raw.tobytes() for t, r in pipe.drain()}
+        barrier()
+        s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+        s0.record(main)
+        for s in pipe.slots:
+            s.stream.wait_event(s0)
+        bad = 0
+        for i in range(ke):
+            fin = pipe.submit_host_scores(h_scores[i % nsb], upw, upb, h_disp[i % nsb], intr, tag=i % nsb)
+            if fin:
+                bad += fin[1].raw.tobytes() != first.get(fin[0], fin[1].raw.tobytes())
+        for tag, res in pipe.drain():
+            bad += res.raw.tobytes() != first.get(tag, res.raw.tobytes())
+        for s in pipe.slots:
+            main.wait_stream(s.stream)
+        s1.record(main)
+        barrier()
+        mismatches += bad
+        e2e_sc = (ke, s0.elapsed_time(s1))
+        pipe.pixel_ms.clear(); pipe.knn_ms.clear(); pipe.total_ms.clear()
+
     # ---- reduce over ranks (max time)
     def max_over_ranks(x):
         if world == 1:
@@ -285,6 +321,8 @@ def run_b200(a):
     elapsed_ms = max_over_ranks(elapsed_ms)
     if e2e:
         e2e = (e2e[0], max_over_ranks(e2e[1]))
+    if e2e_sc:
+        e2e_sc = (e2e_sc[0], max_over_ranks(e2e_sc[1]))
     mism = int(max_over_ranks(float(mismatches)))
 
     if rank == 0:
@@ -364,7 +402,15 @@ def run_b200(a):
             ke, ems = e2e
             line["e2e"] = {"value": ke * B * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * HW * 20,
                            "d2h_bytes_per_step": B * 328, "steps": ke,
+                           "h2d_gb_per_s": ke * B * HW * 20 / (ems * 1e-3) / 1e9,
                            "api": "FramePipeline.submit_host (pinned host inputs, copies pipelined over the slots)"}
+        if e2e_sc:
+            ke, ems = e2e_sc
+            sc_bytes = B * ((H // 8) * (W // 8) * 12 + HW * 8)
+            line["e2e_score_map_mode"] = {"value": ke * B * world / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": sc_bytes,
+                                          "d2h_bytes_per_step": B * 328, "steps": ke,
+                                          "note": "same call with FCN-8s' last transposed convolution fused into the label kernel "
+                                                  "(SURVEY 8a row 1u): scores [H/8,W/8,3] + disparities cross PCIe, logits never exist"}
         if world == 1 and not a.skip_cpu_baseline:
             try:
                 from oracle.cpu_baseline import CpuBaseline

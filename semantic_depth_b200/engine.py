@@ -311,15 +311,19 @@ class FusionEngine:
                            intr: Intrinsics, params: FusionParams | None = None) -> FusionResult:
         """The fused path fed by the unexpanded FCN-8s head (``second_skip`` scores + the transposed-conv kernel of
         fcn8s/fcn.py:207-213): the 12 B/pixel logits tensor is never materialised."""
+        with torch.cuda.device(self.device):
+            return self.fetch(self.enqueue_scores(scores, weights, bias, disp, intr, params))
+
+    def enqueue_scores(self, scores, weights, bias, disp, intr: Intrinsics, params: FusionParams | None = None) -> int:
+        """``enqueue`` for the score-map mode (no host sync; CUDA-graph capturable after one eager call)."""
         params = params or FusionParams()
         sc, upw, upb = scores.contiguous(), weights.contiguous(), bias.contiguous()
         b = self._check_scores(sc, upw, upb, disp)
         cam, ps = camera_struct(intr), params_struct(params)
-        with torch.cuda.device(self.device):
-            check(self.lib.sd_fuse_frames_scores(_ptr(sc), _ptr(upw), _ptr(upb), _ptr(disp), b, self.height, self.width,
-                                                 C.byref(cam), C.byref(ps), _ptr(self._results), self._ws, _stream_ptr()),
-                  "sd_fuse_frames_scores")
-            return self.fetch(b)
+        check(self.lib.sd_fuse_frames_scores(_ptr(sc), _ptr(upw), _ptr(upb), _ptr(disp), b, self.height, self.width,
+                                             C.byref(cam), C.byref(ps), _ptr(self._results), self._ws, _stream_ptr()),
+              "sd_fuse_frames_scores")
+        return b
 
     # ------------------------------------------------------------------------------------------
     # per-call cloud ops (SoA device tensors in, device tensors / host scalars out)

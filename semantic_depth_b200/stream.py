@@ -195,6 +195,45 @@ class FramePipeline:
             self._launch(slot, slot.stage_logits[:b], slot.stage_disp[:b], intr, key=("host", b))
         return finished
 
+    def submit_host_scores(self, scores, weights_dev: torch.Tensor, bias_dev: torch.Tensor, disp, intr: Intrinsics, tag=None):
+        """Host inputs in the score-map mode: ``scores`` [B,H/8,W/8,3] and ``disp`` [B,2,H,W] come from (pinned) host
+        memory, the up-sampling kernel and bias are device-resident model weights.  One CUDA graph per slot."""
+        slot, finished = self._take_slot()
+        sc = scores if isinstance(scores, torch.Tensor) else torch.from_numpy(scores)
+        dp = disp if isinstance(disp, torch.Tensor) else torch.from_numpy(disp)
+        b = sc.shape[0]
+        eng = slot.engine
+        with torch.cuda.stream(slot.stream):
+            if getattr(slot, "stage_scores", None) is None:
+                slot.stage_scores = torch.empty((self.batch, self.height // 8, self.width // 8, 3), dtype=torch.float32, device=self.device)
+            if slot.stage_disp is None:
+                slot.stage_disp = torch.empty((self.batch, 2, self.height, self.width), dtype=torch.float32, device=self.device)
+            slot.stage_scores[:b].copy_(sc, non_blocking=True)
+            slot.stage_disp[:b].copy_(dp, non_blocking=True)
+            slot.tag = tag
+            key = ("host_scores", b, weights_dev.data_ptr())
+            args = (slot.stage_scores[:b], weights_dev, bias_dev, slot.stage_disp[:b], intr, self.params)
+            g = slot.graphs.get(key)
+            if g is None and self.use_graphs:
+                eng.enqueue_scores(*args)                     # eager once: builds the job tables
+                slot.stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=slot.stream):
+                    eng.enqueue_scores(*args)
+                slot.graphs[key] = g
+            if g is not None:
+                g.replay()
+            else:
+                eng.enqueue_scores(*args)
+            slot.nbytes = b * C.sizeof(SdFrameResult)
+            slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
+            if self.timing:                                   # keep the event bookkeeping of _retire valid
+                for e in slot.ev:
+                    e.record(slot.stream)
+            slot.done.record(slot.stream)
+            slot.busy = True
+        return finished
+
     def drain(self):
         out = []
         for _ in range(len(self.slots)):

@@ -19,6 +19,8 @@
 //   pixel_scan_kernel     exclusive scan of the tile counts of a frame (raster order = NumPy order)
 //   pixel_scatter_kernel  blends / reprojects the kept pixels again (cheaper than storing them) and writes
 //                         them at their final raster-ordered position, with their source pixel index
+#include <cmath>
+#include <cstring>
 #include "sd_internal.cuh"
 
 namespace sd {
@@ -107,6 +109,9 @@ struct PixArgs {
     const float* upb;          // [3]
     float* logits_out;         // optional [B][hw][3]: the upsampled logits (parity tests)
     int label_mode;            // 0: softmax > thr (reference), 1: argmax (north_star wording)
+    // z cut as a threshold on the scaled disparity: z(d) = fl32(q23 / (q32 * d)) is monotone in d > 0, so the host finds
+    // the largest fp32 d with z(d) < -cut by bisection over the bit patterns, with the kernel's own arithmetic
+    int use_dstar; uint32_t dstar_bits;
 };
 
 // blended + scaled disparity of one pixel (semantic_depth.py:660-664,676 and :145)
@@ -212,10 +217,15 @@ pixel_label_kernel(const __grid_constant__ PixArgs a) {
             if (lab & 1) {
                 float dpp;
                 const float d = blend_px(a, l4[j], r4[j], u0 + j, dpp);
-                const double wp = q3 * (double)d;
-                const float z = div_to_f32(q2, 1.0 / wp, wp);
+                bool far_enough;
+                if (a.use_dstar) {
+                    far_enough = __float_as_uint(d) <= a.dstar_bits;     // +0 .. d*: z < -cut; negative, NaN: bits above
+                } else {
+                    const double wp = q3 * (double)d;
+                    far_enough = div_to_f32(q2, 1.0 / wp, wp) < -a.road_z_cut;
+                }
                 ++n_road;
-                if (z < -a.road_z_cut) { lab |= 4; ++n_roadz; }          // pcl.py:36
+                if (far_enough) { lab |= 4; ++n_roadz; }                 // pcl.py:36
             }
             n_fence += (lab & 2) ? 1 : 0;
             fl[j] = (unsigned char)lab;
@@ -263,6 +273,7 @@ pixel_scan_kernel(const __grid_constant__ PixArgs a) {
 __global__ void __launch_bounds__(kPixThreads)
 pixel_scatter_kernel(const __grid_constant__ PixArgs a) {
     __shared__ int s_scan[33];
+    __shared__ float4 s_out[2][kPixTile];       // road / fence survivors of the tile in output order
     const int f = blockIdx.y, tile = blockIdx.x, tid = threadIdx.x;
     const bool want_all = (a.points != nullptr) || (a.disp_pp != nullptr);
     const int32_t* tc = a.tcounts + ((size_t)f * a.pix_tiles + tile) * 4;
@@ -309,24 +320,53 @@ pixel_scatter_kernel(const __grid_constant__ PixArgs a) {
     int total;
     const int excl = block_excl_scan(n_roadz | (n_fence << 16), s_scan, &total);
     const int32_t* to = a.toffs + ((size_t)f * a.pix_tiles + tile) * 2;
-    int road_pos = to[0] + (excl & 0xffff), fence_pos = to[1] + (excl >> 16);
-    const size_t cb = (size_t)f * a.cap_stride;
+    // stage the survivors in output order, then leave through coalesced stores
+    int rp = excl & 0xffff, fp = excl >> 16;
 #pragma unroll
     for (int j = 0; j < kPixPer; ++j) {
-        if (fl[j] & 4) {
-            a.road.x[cb + road_pos] = X[j]; a.road.y[cb + road_pos] = Y[j]; a.road.z[cb + road_pos] = Z[j];
-            a.road.src[cb + road_pos] = p + j;
-            ++road_pos;
+        if (fl[j] & 4) { s_out[0][rp] = make_float4(X[j], Y[j], Z[j], __int_as_float(p + j)); ++rp; }
+        if (fl[j] & 2) { s_out[1][fp] = make_float4(X[j], Y[j], Z[j], __int_as_float(p + j)); ++fp; }
+    }
+    __syncthreads();
+    const int n_r = total & 0xffff, n_f = total >> 16;
+    const size_t cb = (size_t)f * a.cap_stride;
+    {
+        const size_t o = cb + to[0];
+        for (int i = tid; i < n_r; i += kPixThreads) {
+            const float4 q = s_out[0][i];
+            a.road.x[o + i] = q.x; a.road.y[o + i] = q.y; a.road.z[o + i] = q.z; a.road.src[o + i] = __float_as_int(q.w);
         }
-        if (fl[j] & 2) {
-            a.fence.x[cb + fence_pos] = X[j]; a.fence.y[cb + fence_pos] = Y[j]; a.fence.z[cb + fence_pos] = Z[j];
-            a.fence.src[cb + fence_pos] = p + j;
-            ++fence_pos;
+    }
+    {
+        const size_t o = cb + to[1];
+        for (int i = tid; i < n_f; i += kPixThreads) {
+            const float4 q = s_out[1][i];
+            a.fence.x[o + i] = q.x; a.fence.y[o + i] = q.y; a.fence.z[o + i] = q.z; a.fence.src[o + i] = __float_as_int(q.w);
         }
     }
 }
 
 }  // namespace sd
+
+// largest fp32 d >= +0 with fl32(q23 / (q32 * d)) < -cut, as a bit pattern (host restatement of the kernel's arithmetic)
+static bool zcut_threshold(float q23, float q32, float cut, uint32_t* bits_out) {
+    if (!(q23 < 0.f) || !(q32 > 0.f) || !(cut >= 0.f) || !std::isfinite(cut)) return false;
+    auto pred = [&](uint32_t b) {
+        float d; memcpy(&d, &b, 4);
+        const double wp = (double)q32 * (double)d;
+        const float z = (float)((double)q23 / wp);
+        return z < -cut;
+    };
+    if (!pred(0u)) return false;                       // +0 -> z = -inf: always true for a sane camera
+    uint32_t lo = 0u, hi = 0x7f800000u;                // pred(lo) true; find the last true pattern up to +inf
+    if (pred(hi)) { *bits_out = hi; return true; }
+    while (hi - lo > 1u) {
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        if (pred(mid)) lo = mid; else hi = mid;
+    }
+    *bits_out = lo;
+    return true;
+}
 
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,
                     int batch, int height, int width, SdCamera cam, double prob_thr, float road_z, int flags,
@@ -350,6 +390,8 @@ int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_
     a.labels = d_labels; a.points = d_points; a.disp_pp = d_disp_pp;
     a.flags = d_flags; a.tcounts = d_tcounts; a.toffs = d_toffs; a.pix_tiles = pix_tiles;
     a.scores = d_scores; a.upw = d_upw; a.upb = d_upb; a.logits_out = d_logits_out; a.label_mode = label_mode;
+    a.dstar_bits = 0u;
+    a.use_dstar = zcut_threshold(cam.q23, cam.q32, road_z, &a.dstar_bits) ? 1 : 0;
     dim3 grid(pix_tiles, batch);
     pixel_label_kernel<<<grid, kPixThreads, 0, st>>>(a);
     pixel_scan_kernel<<<batch, 1024, 0, st>>>(a);

@@ -123,6 +123,7 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->cell_start = c.take<int32_t>(F * ((size_t)ws->cell_cap + 8));
     ws->cell_of = c.take<int32_t>(F * cap);
     ws->sp = c.take<float4>(F * cap * kLevels);
+    ws->cell_box = c.take<uint4>(F * ((size_t)ws->cell_cap / 8 + 64));
     ws->avg = c.take<double>(F * cap);
     ws->cnt = c.take<int32_t>(F * cap);
     ws->gstatus = c.take<unsigned long long>((size_t)F * ws->grid_tiles);
@@ -211,6 +212,7 @@ void fill_knn(KnnJob& j, const float* x, const float* y, const float* z, const i
     j.gs = ws->gs + f;
     j.cell_count = ws->cell_count + oc; j.cell_start = ws->cell_start + oc; j.cell_of = ws->cell_of + o;
     j.sp = ws->sp + o * kLevels;
+    j.cell_box = ws->cell_box + (size_t)f * ((size_t)ws->cell_cap / 8 + 64);
     j.avg = ws->avg + o; j.cnt = ws->cnt + o;
     j.scan_status = ws->gstatus + (size_t)f * ws->grid_tiles; j.scan_ctl = ws->gctl + f;
     j.cell_cap = ws->cell_cap;
@@ -253,6 +255,7 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaMemsetAsync(ws->gstatus, 0, sizeof(unsigned long long) * max_frames * ws->grid_tiles, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->gctl, 0, sizeof(ScanCtl) * max_frames, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->scratch, 0, ws->scratch_bytes, st));
+    { int rc_box = sd_launch_cell_box_init(ws->cell_box, (size_t)max_frames * ((size_t)ws->cell_cap / 8 + 64), st); if (rc_box) return rc_box; }
     // GridState: bbox keys start at (+max, 0); FrameState slab keys likewise
     {
         std::vector<GridState> g(max_frames);
@@ -752,7 +755,6 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
     if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
     }
     if (do_knn && P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
-    if (do_post && P.use_sor && P.use_ror) SD_RUN(sd_launch_sor_stats(T.k_road, B, cap, st));
     if (do_post && P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
     if (do_post) {
         SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
@@ -808,8 +810,7 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
     if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
     if (P->use_sor) n += 1;
-    if (P->use_sor && P->use_ror) n += 1;        // statistical filter applied to the cell-sorted copies
-    if (P->use_ror) n += 1;
+    if (P->use_ror) n += 2;                      // statistical filter applied to the sorted copies + per-cell statistics, radius search
     n += 1 + 1;                                  // final road compaction, slab
     if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain
     n += 1;                                      // finalize

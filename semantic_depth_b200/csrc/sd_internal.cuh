@@ -130,6 +130,7 @@ struct KnnJob {
     int32_t* cell_start;        // [cell_cap + 1] absolute positions into the sorted copies
     int32_t* cell_of;           // [cap] level-0 cell of each point (input order)
     float4* sp;                 // [kLevels * cap] cell-sorted copies (x, y, z, bits(original index)), level L at [L*n, (L+1)*n)
+    uint4* cell_box;            // [cell_cap / 8] per level-1 cell: (alive count, ordered keys of min / max along the collapsed axis, -)
     double* avg;                // [cap] mean kNN distance, by ORIGINAL index
     int32_t* cnt;               // [cap] radius counts, by original index
     unsigned long long* scan_status; ScanCtl* scan_ctl;
@@ -234,7 +235,7 @@ struct SdWorkspace {
     // grid / knn per frame
     sd::GridState* gs;                   // [F]
     int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
-    float4* sp;
+    float4* sp; uint4* cell_box;
     double* avg; int32_t* cnt;
     unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
     // ransac per (frame, chain 0..2)
@@ -257,8 +258,8 @@ int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, cudaStream_t st);
 int sd_launch_slab(const sd::SlabJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
-int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
+int sd_launch_cell_box_init(uint4* d_box, size_t count, cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
 int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,

@@ -44,6 +44,11 @@ grid_bbox_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
     GridState* gs = J.gs;
     const int n = *J.n;
+    {   // the level-1 cell statistics of the previous cloud are no longer needed: back to (0, +max, 0)
+        const int prev1 = gs->ld0[1] * gs->ld1[1];               // read before any block can pass the ticket below
+        for (int c = blockIdx.x * kGridThreads + threadIdx.x; c < prev1; c += gridDim.x * kGridThreads)
+            J.cell_box[c] = make_uint4(0u, 0xffffffffu, 0u, 0u);
+    }
     uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
     for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
         uint32_t k0 = f2key(__ldg(J.x + i)), k1 = f2key(__ldg(J.y + i)), k2 = f2key(__ldg(J.z + i));
@@ -726,16 +731,43 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
 __global__ void __launch_bounds__(kGridThreads)
 sor_mark_kernel(const KnnJob* __restrict__ jobs) {
     const KnnJob J = jobs[blockIdx.y];
-    if (!J.use_sor) return;
-    const int n = J.gs->n;
-    const double thr = J.stats[2];
+    const GridState g = *J.gs;
+    const int n = g.n;
+    const bool sor = J.use_sor != 0;
+    const double thr = sor ? J.stats[2] : 0.0;
+    const float finf = __int_as_float(0x7f800000);
     int alive_local = 0;
-    for (int p = blockIdx.x * kGridThreads + threadIdx.x; p < kLevels * n; p += gridDim.x * kGridThreads) {
-        const int orig = __float_as_int(J.sp[p].w);
-        const double a = J.avg[orig];
-        const bool alive = (a > 0.0 && a < thr);
-        if (!alive) J.sp[p].x = __int_as_float(0x7f800000);
-        if (p < n) { if (!alive) J.cnt[orig] = 0; alive_local += alive ? 1 : 0; }
+    for (int p0 = blockIdx.x * kGridThreads; p0 < kLevels * n; p0 += gridDim.x * kGridThreads) {   // warp-uniform trip count
+        const int p = p0 + threadIdx.x;
+        bool alive = false; float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < kLevels * n) {
+            q = J.sp[p];
+            alive = true;
+            if (sor) {
+                const int orig = __float_as_int(q.w);
+                const double a = J.avg[orig];
+                alive = (a > 0.0 && a < thr);
+                if (!alive) J.sp[p].x = finf;
+                if (p < n) { if (!alive) J.cnt[orig] = 0; alive_local += alive ? 1 : 0; }
+            }
+        }
+        // per level-1 cell: number of alive points and their extent along the collapsed axis (entries are sorted by cell:
+        // the lanes of a cell reduce among themselves, one lane issues the three atomics)
+        const bool l1 = alive && p >= n && p < 2 * n;
+        int cell = -1; uint32_t key = 0u;
+        if (l1) {
+            const int c0 = cell_coord((double)pick_axis(g.a0, q.x, q.y, q.z), g.o0, g.inv_cell, g.d0) >> 2;
+            const int c1 = cell_coord((double)pick_axis(g.a1, q.x, q.y, q.z), g.o1, g.inv_cell, g.d1) >> 2;
+            cell = c1 * g.ld0[1] + c0;
+            key = f2key(pick_axis(g.a2, q.x, q.y, q.z));
+        }
+        const unsigned grp = __match_any_sync(SD_FULL, cell);
+        const uint32_t kmin = __reduce_min_sync(grp, l1 ? key : 0xffffffffu);
+        const uint32_t kmax = __reduce_max_sync(grp, l1 ? key : 0u);
+        if (l1 && lane_id() == __ffs(grp) - 1) {
+            uint4* box = J.cell_box + cell;
+            atomicAdd(&box->x, (unsigned)__popc(grp)); atomicMin(&box->y, kmin); atomicMax(&box->z, kmax);
+        }
     }
     alive_local = warp_sum(alive_local);
     if (lane_id() == 0 && J.n_alive && alive_local) atomicAdd(J.n_alive, alive_local);
@@ -756,6 +788,8 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
     const float r2_in = __double2float_rd(r2 * (1.0 - 3e-6)), r2_out = __double2float_ru(r2 * (1.0 + 3e-6));
     const int cap = J.count_cap;
     const float finf = __int_as_float(0x7f800000);
+    const float r2_sure = __double2float_rd(r2 * (1.0 - 1e-4));
+    const int ga2 = J.gs->a2;
     int Lmax = 0;
 #pragma unroll
     for (int l = 1; l < kLevels; ++l) if (g.cell * (double)(1 << (2 * l)) <= r) Lmax = l;
@@ -771,6 +805,31 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
         if (qx == finf) continue;                               // removed by the statistical filter (count already 0)
         const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
         const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
+        if (cap >= 0) {
+            // whole level-1 cells inside the ball: their alive points count without being looked at
+            const float cell1 = (float)(g.cell * 4.0), qa = pick_axis(ga2, qx, qy, qz);
+            const float f0 = (float)(q0 - g.o0), f1 = (float)(q1 - g.o1);        // query relative to the grid origin
+            const int k0 = c0 >> 2, k1 = c1 >> 2;
+            int sure = 0;
+#pragma unroll
+            for (int dy = -1; dy <= 1; ++dy) {
+#pragma unroll
+                for (int dx = -1; dx <= 1; ++dx) {
+                    const int e0 = k0 + dx, e1 = k1 + dy;
+                    if (e0 < 0 || e0 >= g.d0[1] || e1 < 0 || e1 >= g.d1[1]) continue;
+                    const uint4 bx = __ldg(J.cell_box + e1 * g.d0[1] + e0);
+                    const int na = (int)bx.x;
+                    if (na <= 0) continue;
+                    const float blo = key2f(bx.y), bhi = key2f(bx.z);
+                    const float lo0 = (float)e0 * cell1, lo1 = (float)e1 * cell1;
+                    const float far0 = fmaxf(fabsf(f0 - lo0), fabsf(lo0 + cell1 - f0)) + 1e-4f;
+                    const float far1 = fmaxf(fabsf(f1 - lo1), fabsf(lo1 + cell1 - f1)) + 1e-4f;
+                    const float far2 = fmaxf(fabsf(qa - blo), fabsf(bhi - qa)) + 1e-4f;
+                    if ((far0 * far0 + far1 * far1) + far2 * far2 <= r2_sure) sure += na;
+                }
+            }
+            if (sure > cap) { J.cnt[__float_as_int(qp.w)] = cap + 1; continue; }
+        }
         int L = Lmax;
         if (cap >= 0) {
             int s3[3], e3[3];
@@ -898,11 +957,16 @@ int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStrea
     return launch_knn_t<65>(d_jobs, grid, st);
 }
 
-// cloud statistics are folded into knn_kernel; this applies the resulting threshold to the sorted copies
-int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st) {
-    using namespace sd;
-    if (njobs <= 0) return SD_OK;
-    sor_mark_kernel<<<grid_for(3 * cap, kGridThreads, 4, njobs, 8), kGridThreads, 0, st>>>(d_jobs);
+
+namespace sd {
+__global__ void cell_box_init_kernel(uint4* box, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        box[i] = make_uint4(0u, 0xffffffffu, 0u, 0u);
+}
+}  // namespace sd
+
+int sd_launch_cell_box_init(uint4* d_box, size_t count, cudaStream_t st) {
+    sd::cell_box_init_kernel<<<148 * 4, 256, 0, st>>>(d_box, count);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
@@ -910,6 +974,8 @@ int sd_launch_sor_stats(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st) {
     using namespace sd;
     if (njobs <= 0) return SD_OK;
+    // statistical filter applied to the sorted copies (if any) + per-cell statistics of what is left
+    sor_mark_kernel<<<grid_for(3 * cap, kGridThreads, 4, njobs, 8), kGridThreads, 0, st>>>(d_jobs);
     radius_kernel<<<grid_for(cap, kKnnThreads, 1, njobs, 16), kKnnThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;

@@ -180,6 +180,13 @@ int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_weights, const
                          int32_t* d_counts, uint8_t* d_labels, float* d_points, float* d_disp_pp, float* d_logits_out,
                          SdWorkspace* ws, void* stream);
 
+/* ---- next to the path -------------------------------------------------- */
+/* cv2.resize(frame, (dst_width, dst_height), interpolation=cv2.INTER_CUBIC) on uint8 frames, the first step of
+ * process_frame (semantic_depth.py:110-112): OpenCV's fixed-point definition (11-bit weights, integer passes,
+ * (v + 2^21) >> 22).  d_src [batch][src_height][src_width][channels], d_dst likewise; channels in {1, 3, 4}. */
+int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_width, int channels,
+                       uint8_t* d_dst, int dst_height, int dst_width, void* stream);
+
 /* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
 /* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
 int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream);

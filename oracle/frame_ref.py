@@ -68,6 +68,50 @@ def upsample_scores(scores, weights, bias):
     return out.reshape(H * W, 3)
 
 
+def _cubic_tables(src_n, dst_n):
+    """Tap indices [dst,4] (border-replicated) and 11-bit fixed-point weights [dst,4] of cv2.resize(INTER_CUBIC)."""
+    scale = float(src_n) / dst_n
+    d = np.arange(dst_n, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    x = (f - s.astype(np.float32)).astype(np.float32)
+    one, A = np.float32(1), np.float32(-0.75)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    xm = one - x
+    c2 = ((A + np.float32(2)) * xm - (A + np.float32(3))) * xm * xm + one
+    c3 = one - c0 - c1 - c2
+    co = np.stack([c0, c1, c2, c3], axis=-1).astype(np.float32)
+    ico = np.clip(np.rint(co * np.float32(2048)), -32768, 32767).astype(np.int64)   # saturate_cast<short>(c * 2^11)
+    idx = np.clip(s[:, None] - 1 + np.arange(4)[None, :], 0, src_n - 1)
+    return idx, ico
+
+
+def resize_cubic_u8(img, dst_w, dst_h):
+    """``cv2.resize(frame, (w, h), interpolation=cv2.INTER_CUBIC)`` on uint8 (semantic_depth.py:110-112).
+
+    OpenCV's fixed-point definition: bicubic weights (A = -0.75) evaluated in fp32 and rounded to 11 fractional
+    bits, an integer horizontal pass, an integer vertical pass, ``(v + 2^21) >> 22`` and saturation.  cv2's SIMD
+    builds evaluate the vertical pass in fp32 for the vectorised part of each row, so cv2 itself differs from this
+    definition by at most 1 LSB on a machine-dependent subset of pixels (tests/golden/make_golden.py records it).
+    """
+    img = np.asarray(img, dtype=np.uint8)
+    if img.ndim == 2:
+        img = img[:, :, None]
+    h, w, c = img.shape
+    xi, xa = _cubic_tables(w, dst_w)
+    yi, yb = _cubic_tables(h, dst_h)
+    S = img.astype(np.int64)
+    hor = np.zeros((h, dst_w, c), np.int64)
+    for k in range(4):
+        hor += S[:, xi[:, k], :] * xa[None, :, k, None]
+    out = np.zeros((dst_h, dst_w, c), np.int64)
+    for k in range(4):
+        out += hor[yi[:, k], :, :] * yb[:, k, None, None]
+    out = (out + (1 << 21)) >> 22
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
 def labels_argmax(logits):
     """north_star's wording of the labelling: ``argmax`` over the three classes (first maximum wins, like
     ``np.argmax``); road = class 0, fence = class 1.  An alternative to the reference's ``softmax > 0.5``."""

@@ -391,6 +391,14 @@ extern "C" int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_wei
                            d_fence_src, d_counts, d_labels, d_points, d_disp_pp, d_logits_out, ws, stream);
 }
 
+extern "C" int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_width, int channels,
+                                  uint8_t* d_dst, int dst_height, int dst_width, void* stream) {
+    if (!d_src || !d_dst || batch < 1 || src_height < 1 || src_width < 1 || dst_height < 1 || dst_width < 1)
+        return fail(SD_ERR_INVALID, "sd_resize_cubic_u8: bad argument");
+    if (channels != 1 && channels != 3 && channels != 4) return fail(SD_ERR_UNSUPPORTED, "sd_resize_cubic_u8: channels must be 1, 3 or 4");
+    return sd_launch_resize_cubic_u8(d_src, batch, src_height, src_width, channels, d_dst, dst_height, dst_width, (cudaStream_t)stream);
+}
+
 extern "C" int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream) {
     int rc = check_n(ws, n); if (rc) return rc;
     if (!d_col || !h_out) return fail(SD_ERR_INVALID, "sd_median_mad: null argument");

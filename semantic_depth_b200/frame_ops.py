@@ -49,6 +49,31 @@ def labels_from_logits(logits, shape, prob_thr: float = 0.5):
     return _back((lab & 1) != 0, was_torch), _back((lab & 2) != 0, was_torch)
 
 
+def resize_cubic(frame, size):
+    """``cv2.resize(frame, size, interpolation=cv2.INTER_CUBIC)`` for uint8 frames [H,W,C] or batches [B,H,W,C]
+    (semantic_depth.py:110-112); ``size`` = (width, height) as in OpenCV.  OpenCV's fixed-point definition."""
+    from . import _lib
+    from ._lib import check
+    was_torch = isinstance(frame, torch.Tensor)
+    t = (frame if was_torch else torch.from_numpy(np.ascontiguousarray(frame))).to(device="cuda", dtype=torch.uint8).contiguous()
+    squeeze_c = t.ndim == 2
+    if squeeze_c:
+        t = t[:, :, None]
+    batched = t.ndim == 4
+    if not batched:
+        t = t[None]
+    b, h, w, c = t.shape
+    dw, dh = int(size[0]), int(size[1])
+    out = torch.empty((b, dh, dw, c), dtype=torch.uint8, device=t.device)
+    with torch.cuda.device(t.device):
+        check(_lib.load().sd_resize_cubic_u8(t.data_ptr(), b, h, w, c, out.data_ptr(), dh, dw,
+                                             torch.cuda.current_stream().cuda_stream), "sd_resize_cubic_u8")
+    out = out if batched else out[0]
+    if squeeze_c:
+        out = out[..., 0]
+    return _back(out, was_torch)
+
+
 def upsample_scores(scores, weights, bias):
     """FCN-8s' last layer, ``conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same')`` (fcn8s/fcn.py:207-213):
     scores [h,w,3] -> logits [8h*8w, 3] fp32, evaluated by the label kernel (fp32, fixed summation order)."""

@@ -6,6 +6,7 @@ compute_3D_points (lifted with ast, real cv2) and the oracle were asserted bit-e
 re-checked against those vectors (the reference does not exist on the GPU box)."""
 import glob
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -136,3 +137,17 @@ def test_argmax_labels_oracle():
     road, fence = frame_ref.labels_argmax(lg)
     assert road.tolist() == [True, False, False, True, False, True]      # first maximum wins; NaN wins like np.argmax
     assert fence.tolist() == [False, True, False, False, True, False]
+
+
+def test_resize_oracle_against_cv2_golden(golden_dir):
+    """the fixed-point bicubic resize against outputs of the real cv2 (<= 1 LSB, see make_golden_resize.py)."""
+    sys.path.insert(0, golden_dir)
+    from make_golden_resize import make_image
+    z = np.load(os.path.join(golden_dir, "resize_vectors.npz"))
+    n = len([k for k in z.files if k.endswith("_shape")])
+    assert n >= 4
+    for i in range(n):
+        h, w, dh, dw, c, seed = (int(v) for v in z[f"case{i}_shape"])
+        got = frame_ref.resize_cubic_u8(make_image(h, w, c, seed), dw, dh)
+        d = np.abs(got.astype(int) - z[f"case{i}_cv2"].astype(int))
+        assert got.shape == (dh, dw, c) and d.max() <= 1 and (d > 0).mean() < 0.1

@@ -124,6 +124,8 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->cell_of = c.take<int32_t>(F * cap);
     ws->sp = c.take<float4>(F * cap * kLevels);
     ws->cell_box = c.take<uint4>(F * ((size_t)ws->cell_cap / 8 + 64));
+    ws->ybox = c.take<uint2>(F * ((size_t)ws->cell_cap / 8 + 64));
+    ws->queue = c.take<int32_t>(F * cap); ws->queue_band = c.take<float>(F * cap);
     ws->avg = c.take<double>(F * cap);
     ws->cnt = c.take<int32_t>(F * cap);
     ws->gstatus = c.take<unsigned long long>((size_t)F * ws->grid_tiles);
@@ -213,6 +215,8 @@ void fill_knn(KnnJob& j, const float* x, const float* y, const float* z, const i
     j.cell_count = ws->cell_count + oc; j.cell_start = ws->cell_start + oc; j.cell_of = ws->cell_of + o;
     j.sp = ws->sp + o * kLevels;
     j.cell_box = ws->cell_box + (size_t)f * ((size_t)ws->cell_cap / 8 + 64);
+    j.ybox = ws->ybox + (size_t)f * ((size_t)ws->cell_cap / 8 + 64);
+    j.queue = ws->queue + o; j.queue_band = ws->queue_band + o;
     j.avg = ws->avg + o; j.cnt = ws->cnt + o;
     j.scan_status = ws->gstatus + (size_t)f * ws->grid_tiles; j.scan_ctl = ws->gctl + f;
     j.cell_cap = ws->cell_cap;
@@ -255,6 +259,7 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaMemsetAsync(ws->gstatus, 0, sizeof(unsigned long long) * max_frames * ws->grid_tiles, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->gctl, 0, sizeof(ScanCtl) * max_frames, st));
     SD_CUDA_TRY(cudaMemsetAsync(ws->scratch, 0, ws->scratch_bytes, st));
+    { int rc_yb = sd_launch_ybox_init(ws->ybox, (size_t)max_frames * ((size_t)ws->cell_cap / 8 + 64), st); if (rc_yb) return rc_yb; }
     { int rc_box = sd_launch_cell_box_init(ws->cell_box, (size_t)max_frames * ((size_t)ws->cell_cap / 8 + 64), st); if (rc_box) return rc_box; }
     // GridState: bbox keys start at (+max, 0); FrameState slab keys likewise
     {
@@ -817,7 +822,7 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     int n = 3;                                   // pixel stage: label, scan, scatter
     n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
     if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
-    if (P->use_sor) n += 1;
+    if (P->use_sor) n += 2;                      // k-NN: main kernel + heavy queries
     if (P->use_ror) n += 2;                      // statistical filter applied to the sorted copies + per-cell statistics, radius search
     n += 1 + 1;                                  // final road compaction, slab
     if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain

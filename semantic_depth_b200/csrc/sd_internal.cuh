@@ -120,6 +120,7 @@ struct GridState {
     double ext2;                // extent of the collapsed axis (for the 2D-inside shortcut)
     unsigned long long acc[3][2];  // exact 128-bit fixed-point sums of avg, avg^2 (lo, hi) and the count of avg > 0
     int32_t work;                  // dynamic work counter of the search kernels (next unclaimed sorted index)
+    int32_t qn, qhead;             // queue of the heavy k-NN queries: entries written / entries claimed
     int32_t pad_;
     unsigned long long dbg[8];     // developer counters (see sd_ws_debug_counters)
 };
@@ -130,6 +131,8 @@ struct KnnJob {
     int32_t* cell_start;        // [cell_cap + 1] absolute positions into the sorted copies
     int32_t* cell_of;           // [cap] level-0 cell of each point (input order)
     float4* sp;                 // [kLevels * cap] cell-sorted copies (x, y, z, bits(original index)), level L at [L*n, (L+1)*n)
+    uint2* ybox;                // [cell_cap / 8] per level-1 / level-2 cell: ordered keys of min / max along the collapsed axis, all points
+    int32_t* queue; float* queue_band;   // [cap] heavy k-NN queries: level-0 sorted index, bound of the k-th squared distance
     uint4* cell_box;            // [cell_cap / 8] per level-1 cell: (alive count, ordered keys of min / max along the collapsed axis, -)
     double* avg;                // [cap] mean kNN distance, by ORIGINAL index
     int32_t* cnt;               // [cap] radius counts, by original index
@@ -235,7 +238,7 @@ struct SdWorkspace {
     // grid / knn per frame
     sd::GridState* gs;                   // [F]
     int32_t* cell_count; int32_t* cell_start; int32_t* cell_of;
-    float4* sp; uint4* cell_box;
+    float4* sp; uint4* cell_box; uint2* ybox; int32_t* queue; float* queue_band;
     double* avg; int32_t* cnt;
     unsigned long long* gstatus; sd::ScanCtl* gctl; int grid_tiles;
     // ransac per (frame, chain 0..2)
@@ -260,6 +263,7 @@ int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStrea
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);
 int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_cell_box_init(uint4* d_box, size_t count, cudaStream_t st);
+int sd_launch_ybox_init(uint2* d_box, size_t count, cudaStream_t st);
 int sd_launch_resize_cubic_u8(const uint8_t* d_src, int batch, int src_h, int src_w, int channels, uint8_t* d_dst, int dst_h, int dst_w,
                               cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);

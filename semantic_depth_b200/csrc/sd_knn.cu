@@ -48,6 +48,9 @@ grid_bbox_kernel(const KnnJob* __restrict__ jobs) {
         const int prev1 = gs->ld0[1] * gs->ld1[1];               // read before any block can pass the ticket below
         for (int c = blockIdx.x * kGridThreads + threadIdx.x; c < prev1; c += gridDim.x * kGridThreads)
             J.cell_box[c] = make_uint4(0u, 0xffffffffu, 0u, 0u);
+        const int prevc = gs->ncells - gs->loff[1];               // coarse cells (levels >= 1) of the previous grid
+        for (int c = blockIdx.x * kGridThreads + threadIdx.x; c < prevc; c += gridDim.x * kGridThreads)
+            J.ybox[c] = make_uint2(0xffffffffu, 0u);
     }
     uint32_t mn[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, mx[3] = {0u, 0u, 0u};
     for (int i = blockIdx.x * kGridThreads + threadIdx.x; i < n; i += gridDim.x * kGridThreads) {
@@ -189,10 +192,23 @@ grid_scatter_kernel(const KnnJob* __restrict__ jobs) {
             const int pos = J.cell_start[c] + atomicSub(&J.cell_count[c], 1) - 1;
             J.sp[pos] = pt;
         }
+        const uint32_t akey = f2key(pick_axis(g.a2, x, y, z));
 #pragma unroll
         for (int L = 1; L < kLevels; ++L) {
             const int cl = g.loff[L] + (c1 >> (2 * L)) * g.ld0[L] + (c0 >> (2 * L));
-            const int pos = J.cell_start[cl] + aggregated_add(&J.cell_count[cl], -1) - 1;
+            // the lanes of a coarse cell elect a leader for the position counter and for the cell's extent along the
+            // collapsed axis (ordered keys; a superset bound for any later subset of the cell's points)
+            const unsigned mask = __match_any_sync(__activemask(), cl);
+            const int leader = __ffs(mask) - 1, lane = lane_id();
+            const uint32_t kmin = __reduce_min_sync(mask, akey), kmax = __reduce_max_sync(mask, akey);
+            int old = 0;
+            if (lane == leader) {
+                old = atomicSub(&J.cell_count[cl], __popc(mask));
+                uint2* yb = J.ybox + (cl - g.loff[1]);
+                atomicMin(&yb->x, kmin); atomicMax(&yb->y, kmax);
+            }
+            old = __shfl_sync(mask, old, leader);
+            const int pos = J.cell_start[cl] + old - __popc(mask & ((1u << lane) - 1u)) - 1;
             J.sp[pos] = pt;
         }
     }
@@ -440,13 +456,25 @@ __device__ __forceinline__ void row_run(const GridRt& g, const LevelRt& lv, doub
               cb = cell_coord(q0 + half, g.o0, g.inv_cell, g.d0[0]) >> lv.shift;
     s = __ldg(lv.cs + row * lv.d0 + ca); e = __ldg(lv.cs + row * lv.d0 + cb + 1);
 }
+// warp-reduce the exact partial sums of the cloud statistics and add them to the job's accumulators
+__device__ __forceinline__ void flush_stats(GridState* gs, U128 acc_sum, U128 acc_sq, unsigned long long acc_pos) {
+    acc_sum = warp_sum128(acc_sum); acc_sq = warp_sum128(acc_sq);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc_pos += __shfl_xor_sync(SD_FULL, acc_pos, o);
+    if (lane_id() == 0 && acc_pos) {
+        atomic_add128(gs->acc[0], acc_sum); atomic_add128(gs->acc[1], acc_sq);
+        atomicAdd(&gs->acc[2][0], acc_pos);
+    }
+}
+
 #ifndef SD_KNN_HEAVY
 #define SD_KNN_HEAVY 192
 #endif
 constexpr int kHeavy = SD_KNN_HEAVY;            // a disc with more candidates than this is swept by the whole warp
+constexpr int kExtreme = 4096;                  // ... and beyond this it goes to knn_heavy_kernel (3-D cell pruning, exact re-bounding)
 
 #ifndef SD_KNN_MINB
-#define SD_KNN_MINB 1
+#define SD_KNN_MINB 4
 #endif
 template <int KS>
 __global__ void __launch_bounds__(kKnnThreads, (KS <= 11 ? SD_KNN_MINB : 1))
@@ -543,14 +571,18 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 }
             }
         }
-        // ---- phase 2: collect everything inside the bound.  Lanes with an ordinary disc sweep it themselves;
-        //      a lane whose disc holds many candidates (an outlier above / below a dense region: the grid is 2-D)
-        //      is served by the whole warp, 32 candidates per step.  A list overflow tightens the bound from the
-        //      listed keys and sweeps again.
+        // ---- phase 2: collect everything inside the bound.  Lanes with an ordinary disc sweep it themselves; a lane
+        //      whose disc holds many candidates (an outlier above / below a dense region: the grid is 2-D) is served by
+        //      the whole warp, 32 candidates per step.  A list overflow tightens the bound from the listed keys and
+        //      sweeps once more.  Extreme discs (more than kExtreme candidates or more than kMaxRows rows) and lists that
+        //      still overflow go to knn_heavy_kernel through the job's queue, with the bound.
         int cnt = 0;
+        bool queued = false;
+        float queue_band = __int_as_float(0x7f800000);
         {
             bool todo = (keff > 0 && fed >= keff);
-            float band = todo ? net.get(keff - 1) * (1.0f + 4.0f * kKeyErr) : 0.f;
+            float band = todo ? net.get(keff - 1) * (1.0f + 4.0f * kKeyErr) : __int_as_float(0x7f800000);
+            if (!todo && keff > 0) queued = true;          // no bound at all (cannot happen for keff <= n)
             for (int attempt = 0;; ++attempt) {
                 const double rad = sqrt((double)band) * (1.0 + 1e-9) + g.slack;
                 // sweep level: the finest one on which the disc spans at most 7 rows
@@ -570,7 +602,8 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                             if (e > s) { s_seg[nruns][tid] = make_int2(s, e); ++nruns; total += e - s; }
                         }
                         heavy = total > kHeavy;
-                    } else heavy = true;
+                        if (total > kExtreme) { queued = true; todo = false; }
+                    } else { queued = true; todo = false; }
                 }
                 if (todo) cnt = 0;
                 if (todo && !heavy) {
@@ -623,8 +656,9 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                     __syncwarp();
                     if (lane_id() == ld) cnt = hcnt;
                 }
-                // overflow: the k-th smallest of the listed kListCap (>= k) keys is a tighter bound
-                todo = todo && cnt > kListCap && attempt < 3;
+                // overflow: the k-th smallest of the listed kListCap (>= k) keys is a tighter bound (one retry, then the queue)
+                if (todo && cnt > kListCap && attempt >= 1) { queued = true; todo = false; }
+                todo = todo && cnt > kListCap;
                 if (!__any_sync(SD_FULL, todo)) break;
                 if (todo) {
                     net.init();
@@ -632,12 +666,25 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                     band = fminf(band, net.get(keff - 1) * (1.0f + 4.0f * kKeyErr));
                 }
             }
+            queue_band = band;
         }
+        {
+            queued = queued && valid;
+            const unsigned qm = __ballot_sync(SD_FULL, queued);
+            if (qm) {
+                int qbase = 0;
+                if (lane_id() == __ffs(qm) - 1) qbase = atomicAdd(&J.gs->qn, __popc(qm));
+                qbase = __shfl_sync(SD_FULL, qbase, __ffs(qm) - 1);
+                if (queued) {
+                    const int slot = qbase + __popc(qm & ((1u << lane_id()) - 1u));
+                    J.queue[slot] = i; J.queue_band[slot] = queue_band;
+                }
+            }
+        }
+        if (queued || !valid) continue;             // lanes past the end only shadowed the last query
         // ---- phase 3
-        double sum;
-        if (cnt > kListCap || cnt < keff) {
-            sum = knn_exact_sum<KN>(J, g, qx, qy, qz, q0, q1, c0, c1, keff);
-        } else {
+        double sum = 0.0;
+        if (keff > 0) {
             UNetK<KN + 1> un; un.init();
             for (int e0 = 0; e0 < cnt; e0 += kBatch) {
                 float4 c[kBatch];
@@ -692,20 +739,170 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
         if (valid && avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
     }
 
-    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums.
-    //      Warps retire independently (no CTA barrier): the last WARP of the job finalises.
-    acc_sum = warp_sum128(acc_sum); acc_sq = warp_sum128(acc_sq);
+    // ---- partial cloud statistics (exact integer sums); knn_heavy_kernel adds its queries and finalises
+    flush_stats(J.gs, acc_sum, acc_sq, acc_pos);
+}
+
+// ---- heavy queries ----------------------------------------------------------------------------------------------------
+// One queued query per warp at a time.  The cells of the disc's bounding square (level 1 for discs up to 6 level-1 cells in
+// radius, else level 2) are tested against the query as 3-D boxes -- cell x extent of its points along the collapsed axis --
+// one cell per lane; only cells whose box reaches into the ball are swept, 32 candidates per step.
+//   collect : in-band candidates are ballot-appended to the warp's list;
+//   select  : (after an overflow) every in-band key goes through per-lane networks, the global k-th smallest key is popped
+//             from the 32 networks and becomes the exact bound for a second collect;
+//   answer  : fp64 distances of the listed candidates, one or two per lane; the k smallest are popped in ascending order
+//             and their square roots summed from 0.0 by lane 0 -- the oracle's arithmetic.
+// A list that still overflows (more than kHeavyList - k exact ties) goes to the fp64 ring search.  The last warp finalises
+// the cloud statistics of the job.
+constexpr int kHeavyList = 64;
+constexpr int kHeavyWarps = 4;
+
+template <typename Visit>
+__device__ __forceinline__ void heavy_for_cells(const KnnJob& J, const GridRt& g, int ga2, float hx, float hy, float hz,
+                                                double h0, double h1, float band, Visit&& visit) {
+    const double rad = sqrt((double)band) * (1.0 + 1e-9) + g.slack;
+    if (rad * g.inv_cell < 6.0) {
+        // small disc (under 1.5 level-1 cells): one run per grid row on the finest level where it spans at most 7 rows
+        int Ls = kLevels - 1;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc_pos += __shfl_xor_sync(SD_FULL, acc_pos, o);
-    int last = 0;
-    if (lane_id() == 0) {
-        if (acc_pos) {
-            atomic_add128(J.gs->acc[0], acc_sum); atomic_add128(J.gs->acc[1], acc_sq);
-            atomicAdd(&J.gs->acc[2][0], acc_pos);
+        for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(3 << (2 * l))) Ls = l;
+        const LevelRt lv = level_of(J, g, Ls);
+        const int k1 = cell_coord(h1, g.o1, g.inv_cell, g.d1[0]) >> lv.shift;
+        const int R = (int)(rad * lv.inv_cell) + 1;
+        const int rlo = max(k1 - R, 0), rhi = min(k1 + R, lv.d1 - 1);
+        int ms = 0, me = 0;
+        if (rlo + lane_id() <= rhi) row_run(g, lv, h0, h1, rad, k1, rlo + lane_id(), ms, me);     // at most 9 rows
+        for (unsigned am = __ballot_sync(SD_FULL, me > ms); am; am &= am - 1) {
+            const int r = __ffs(am) - 1;
+            visit(__shfl_sync(SD_FULL, ms, r), __shfl_sync(SD_FULL, me, r));
         }
+        return;
+    }
+    const int hL = (rad * g.inv_cell < 24.0) ? 1 : 2;
+    const LevelRt hv = level_of(J, g, hL);
+    const uint2* ybox = J.ybox + (g.off[hL] - g.off[1]);
+    const double ha = (double)pick_axis(ga2, hx, hy, hz);
+    const int x0 = cell_coord(h0 - rad, g.o0, g.inv_cell, g.d0[0]) >> hv.shift, x1 = cell_coord(h0 + rad, g.o0, g.inv_cell, g.d0[0]) >> hv.shift;
+    const int y0 = cell_coord(h1 - rad, g.o1, g.inv_cell, g.d1[0]) >> hv.shift, y1 = cell_coord(h1 + rad, g.o1, g.inv_cell, g.d1[0]) >> hv.shift;
+    const int ncw = x1 - x0 + 1, total_cells = ncw * (y1 - y0 + 1);
+    for (int base = 0; base < total_cells; base += 32) {
+        const int ci = base + lane_id();
+        int ms = 0, me = 0;
+        if (ci < total_cells) {
+            const int cy = y0 + ci / ncw, cx = x0 + (ci - (ci / ncw) * ncw);
+            const int cell = cy * hv.d0 + cx;
+            const int s = __ldg(hv.cs + cell), e = __ldg(hv.cs + cell + 1);
+            if (e > s) {
+                const uint2 yb = __ldg(ybox + cell);
+                const double lo0 = g.o0 + (double)cx * hv.cell, lo1 = g.o1 + (double)cy * hv.cell;
+                const double d0 = fmax(0.0, fmax(lo0 - h0, h0 - (lo0 + hv.cell)) - g.slack);
+                const double d1 = fmax(0.0, fmax(lo1 - h1, h1 - (lo1 + hv.cell)) - g.slack);
+                const double d2 = fmax(0.0, fmax((double)key2f(yb.x) - ha, ha - (double)key2f(yb.y)));
+                if ((d0 * d0 + d1 * d1 + d2 * d2) * (1.0 - 1e-9) <= (double)band) { ms = s; me = e; }
+            }
+        }
+        for (unsigned am = __ballot_sync(SD_FULL, me > ms); am; am &= am - 1) {
+            const int r = __ffs(am) - 1;
+            visit(__shfl_sync(SD_FULL, ms, r), __shfl_sync(SD_FULL, me, r));
+        }
+    }
+}
+
+template <int KS>
+__global__ void __launch_bounds__(kHeavyWarps * 32)
+knn_heavy_kernel(const KnnJob* __restrict__ jobs) {
+    constexpr int K = KS - 1;
+    constexpr int KN = K > 0 ? K : 1;
+    __shared__ int s_hl[kHeavyWarps][kHeavyList];
+    const KnnJob J = jobs[blockIdx.y];
+    const GridRt g = load_grid(J.gs);
+    const int keff = min(J.k, g.n);
+    const int ga2 = J.gs->a2;
+    const int w = warp_id(), lane = lane_id();
+    const int qn = J.gs->qn;                                      // complete: the main kernel has finished
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    U128 acc_sum{0ull, 0ull}, acc_sq{0ull, 0ull};
+    unsigned long long acc_pos = 0ull;
+    while (true) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&J.gs->qhead, 1);
+        e = __shfl_sync(SD_FULL, e, 0);
+        if (e >= qn) break;
+        const int i = J.queue[e];
+        float band = J.queue_band[e];
+        const float4 qp = __ldg(J.sp + i);
+        const float hx = qp.x, hy = qp.y, hz = qp.z;
+        const double h0 = (double)pick_axis(g.a0, hx, hy, hz), h1 = (double)pick_axis(g.a1, hx, hy, hz);
+        int cnt = 0;
+        for (int pass = 0; pass < 3; ++pass) {
+            if (pass == 1) {
+                // select: exact k-th smallest key of the whole disc
+                FNet<KN> net; net.init();
+                heavy_for_cells(J, g, ga2, hx, hy, hz, h0, h1, band, [&](int s, int e2) {
+                    for (int j = s + lane; j < e2; j += 32) {
+                        const float key = key_of(__ldg(J.sp + j), hx, hy, hz);
+                        if (key <= band) net.feed(key);
+                    }
+                });
+                int head = 0; uint32_t kth = 0x7f800000u;
+                for (int t = 0; t < keff; ++t) {
+                    const uint32_t mine = (head < KN) ? __float_as_uint(net.get(head)) : 0x7f800000u;   // keys >= 0: bit order = value order
+                    kth = __reduce_min_sync(SD_FULL, mine);
+                    const unsigned who = __ballot_sync(SD_FULL, mine == kth);
+                    if (lane == __ffs(who) - 1) ++head;
+                }
+                if (kth < 0x7f800000u) band = fminf(band, __uint_as_float(kth) * (1.0f + 4.0f * kKeyErr));
+                continue;
+            }
+            cnt = 0;
+            heavy_for_cells(J, g, ga2, hx, hy, hz, h0, h1, band, [&](int s, int e2) {
+                for (int j0 = s; j0 < e2; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool in = (j < e2) && key_of(__ldg(J.sp + min(j, e2 - 1)), hx, hy, hz) <= band;
+                    const unsigned bm = __ballot_sync(SD_FULL, in);
+                    const int slot = cnt + __popc(bm & ((1u << lane) - 1u));
+                    if (in && slot < kHeavyList) s_hl[w][slot] = j;
+                    cnt += __popc(bm);
+                }
+            });
+            __syncwarp();
+            if (cnt <= kHeavyList) break;
+        }
+        double sum = 0.0;
+        if (cnt > kHeavyList || cnt < keff) {                     // massive ties (or no finite bound): fp64 ring search
+            if (lane == 0) {
+                const int c0 = cell_coord(h0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(h1, g.o1, g.inv_cell, g.d1[0]);
+                sum = knn_exact_sum<KN>(J, g, hx, hy, hz, h0, h1, c0, c1, keff);
+            }
+        } else {
+            // answer: up to two listed candidates per lane in fp64, k pops of the global minimum in ascending order
+            double v0 = inf, v1 = inf;
+            if (lane < cnt) v0 = dist2_f64(J, s_hl[w][lane], hx, hy, hz);
+            if (lane + 32 < cnt) v1 = dist2_f64(J, s_hl[w][lane + 32], hx, hy, hz);
+            if (v1 < v0) { const double t = v0; v0 = v1; v1 = t; }
+            for (int t = 0; t < keff; ++t) {
+                double m = v0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(SD_FULL, m, o));
+                const unsigned who = __ballot_sync(SD_FULL, v0 == m);
+                if (lane == __ffs(who) - 1) { v0 = v1; v1 = inf; }
+                sum = sum + sqrt(m);                              // every lane keeps the same running sum
+            }
+        }
+        sum = __shfl_sync(SD_FULL, sum, 0);
+        if (lane == 0) {
+            const double avg = (keff > 0) ? sum / (double)keff : -1.0;
+            J.avg[__float_as_int(qp.w)] = avg;
+            if (avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
+        }
+        __syncwarp();
+    }
+    // ---- cloud statistics (Open3D: mean over avg > 0 divided by n, Bessel std): exact integer sums.
+    //      Warps retire independently (no CTA barrier): the last WARP of the job finalises and resets the job's counters.
+    flush_stats(J.gs, acc_sum, acc_sq, acc_pos);
+    if (lane == 0) {
         __threadfence();
-        last = (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * (kKnnThreads / 32) - 1);
-        if (last) {
+        if (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * kHeavyWarps - 1) {
             __threadfence();
             GridState* gs = J.gs;
             const double S = fixed70_to_double(__ldcg(&gs->acc[0][0]), __ldcg(&gs->acc[0][1]));
@@ -719,7 +916,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
             if (sq < 0.0) sq = 0.0;
             const double sd_ = (g.n > 1) ? sqrt(sq / (n - 1.0)) : __longlong_as_double(0x7ff8000000000000ull);
             J.stats[0] = mean; J.stats[1] = sd_; J.stats[2] = mean + J.std_ratio * sd_;
-            gs->ticket = 0; gs->work = 0;
+            gs->ticket = 0; gs->work = 0; gs->qn = 0; gs->qhead = 0;
         }
     }
 }
@@ -939,6 +1136,7 @@ static int launch_knn_t(const sd::KnnJob* d_jobs, dim3 grid, cudaStream_t st) {
         configured = true;
     }
     knn_kernel<KS><<<grid, kKnnThreads, smem, st>>>(d_jobs);
+    knn_heavy_kernel<KS><<<dim3(max(1u, min(grid.x, (148u * 6u) / grid.y)), grid.y), kHeavyWarps * 32, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }
@@ -964,6 +1162,19 @@ __global__ void cell_box_init_kernel(uint4* box, size_t count) {
         box[i] = make_uint4(0u, 0xffffffffu, 0u, 0u);
 }
 }  // namespace sd
+
+namespace sd {
+__global__ void ybox_init_kernel(uint2* box, size_t count) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+        box[i] = make_uint2(0xffffffffu, 0u);
+}
+}  // namespace sd
+
+int sd_launch_ybox_init(uint2* d_box, size_t count, cudaStream_t st) {
+    sd::ybox_init_kernel<<<148 * 4, 256, 0, st>>>(d_box, count);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
 
 int sd_launch_cell_box_init(uint4* d_box, size_t count, cudaStream_t st) {
     sd::cell_box_init_kernel<<<148 * 4, 256, 0, st>>>(d_box, count);

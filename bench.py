@@ -382,9 +382,9 @@ def run_b200(a):
             "host_wall_ms": wall * 1e3,
             "batch_latency_ms": {"mean": float(np.mean(total_ms)) if total_ms else None,
                                  "note": "first to last kernel of one batch, CUDA events, while other batches overlap"},
-            "roofline": {"kernel": "sd::knn_kernel<11> (dominant kernel of the step, profiles/r1_launches.csv)", "bound": "hbm",
+            "roofline": {"kernel": "sd::knn_kernel<11> + its heavy-query pass sd::knn_heavy_kernel<11> (dominant kernel of the step, profiles/r1_launches_summary.txt)", "bound": "hbm",
                          "achieved": knn_ach, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": (knn_ach / peak_gbs) if knn_ach else None, "traffic": traffic_of("knn_kernel"),
+                         "frac": (knn_ach / peak_gbs) if knn_ach else None, "traffic": traffic_of("knn_stage"),
                          "algorithmic_bytes_per_launch": knn_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
                          "note": "exact k-NN on an L1/L2-resident cloud: bound by instruction issue and cache latency, not by "
                                  "HBM (DESIGN.md 3); kernel time measured with CUDA events while other batches' kernels run"},

@@ -292,10 +292,6 @@ int sd_ws_enable_timing(SdWorkspace* ws, int enable);
 int sd_ws_set_stage_mask(SdWorkspace* ws, int mask);
 int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms);
 
-/* Developer counters of the neighbour search of `frame` (cumulative since sd_ws_create; all zero unless the
- * library was built with -DSD_KNN_STATS).  Synchronises the device. */
-int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8);
-
 /* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):
  * which = 0 road (after ROR), 1 left fence (after plane filter), 2 right fence. */
 int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,

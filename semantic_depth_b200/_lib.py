@@ -96,7 +96,6 @@ SIGNATURES = {
     "sd_ws_enable_timing": (_I, [_P, _I]),
     "sd_ws_set_stage_mask": (_I, [_P, _I]),
     "sd_ws_stage_elapsed_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
-    "sd_ws_debug_counters": (_I, [_P, _I, C.POINTER(C.c_ulonglong)]),
     "sd_ws_cloud": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sd_ws_stage_src": (_I, [_P, _I, _I, C.POINTER(_P)]),
 }

@@ -866,13 +866,6 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
     return SD_OK;
 }
 
-extern "C" int sd_ws_debug_counters(SdWorkspace* ws, int frame, unsigned long long* h_out8) {
-    if (!ws || !h_out8 || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_debug_counters: bad argument");
-    SD_CUDA_TRY(cudaDeviceSynchronize());
-    SD_CUDA_TRY(cudaMemcpy(h_out8, ws->gs[frame].dbg, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost));
-    return SD_OK;
-}
-
 extern "C" int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,
                            const int32_t** d_src, const int32_t** d_n) {
     if (!ws || frame < 0 || frame >= ws->max_frames || which < 0 || which > 2) return fail(SD_ERR_INVALID, "sd_ws_cloud: bad argument");

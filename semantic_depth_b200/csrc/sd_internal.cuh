@@ -122,7 +122,6 @@ struct GridState {
     int32_t work;                  // dynamic work counter of the search kernels (next unclaimed sorted index)
     int32_t qn, qhead;             // queue of the heavy k-NN queries: entries written / entries claimed
     int32_t pad_;
-    unsigned long long dbg[8];     // developer counters (see sd_ws_debug_counters)
 };
 struct KnnJob {
     const float* x; const float* y; const float* z; const int32_t* n;

@@ -219,12 +219,6 @@ class FusionEngine:
         check(self.lib.sd_ws_stage_elapsed_ms(self._ws, {"pixel": 0, "total": 1}[which], C.byref(ms)), "sd_ws_stage_elapsed_ms")
         return float(ms.value)
 
-    def debug_counters(self, frame: int = 0) -> dict:
-        out = (C.c_ulonglong * 8)()
-        check(self.lib.sd_ws_debug_counters(self._ws, frame, out), "sd_ws_debug_counters")
-        names = tuple(f"c{i}" for i in range(8))
-        return {n: int(v) for n, v in zip(names, out)}
-
     def final_cloud(self, frame: int, which: str = "road"):
         """(points [N,3] fp32, src [N] int32) of a frame's final road / left / right cloud (device)."""
         idx = {"road": 0, "left": 1, "right": 2}[which]

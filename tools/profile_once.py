@@ -14,4 +14,3 @@ dl, dd = torch.from_numpy(lg).cuda(), torch.from_numpy(dp).cuda()
 for _ in range(2):
     res = eng.fuse_frames(dl, dd, intr, FusionParams())
 print(res.rw, res.f2f, res.counts(0))
-print('debug counters (2 calls):', eng.debug_counters(0))

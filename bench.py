@@ -247,6 +247,16 @@ def run_b200(a):
     knn_ms = list(pipe.knn_ms)
     total_ms = list(pipe.total_ms)
 
+    # ---- the same two segments with nothing else on the GPU (one batch at a time): what the kernels take by themselves
+    iso_pixel, iso_knn = [], []
+    if not a.no_kernel_timing:
+        pipe.pixel_ms.clear(); pipe.knn_ms.clear(); pipe.total_ms.clear()
+        for i in range(min(12, max(3, a.steps))):
+            pipe.submit_device(d_logits[i % nb], d_disp[i % nb], intr, tag=i % nb)
+            pipe.drain()
+        iso_pixel, iso_knn = list(pipe.pixel_ms), list(pipe.knn_ms)
+        pipe.pixel_ms.clear(); pipe.knn_ms.clear(); pipe.total_ms.clear()
+
     # ---- end to end: pinned host inputs -> H2D -> fused path -> D2H of the answers, pipelined over the slots
     e2e = None
     if not a.skip_e2e:
@@ -362,6 +372,9 @@ def run_b200(a):
             return float(t) if t is not None else None
 
         knn_ach, pix_ach = gbs(knn_bytes, k_ms), gbs(pix_bytes, pix_ms)
+        k_iso = float(np.mean(iso_knn)) if iso_knn else float("nan")
+        p_iso = float(np.mean(iso_pixel)) if iso_pixel else float("nan")
+        knn_iso_ach, pix_iso_ach = gbs(knn_bytes, k_iso), gbs(pix_bytes, p_iso)
         frames = a.steps * B * world
         value = frames / (elapsed_ms * 1e-3)
         alg_path = float(np.mean(per_batch_alg)) / B
@@ -386,12 +399,16 @@ def run_b200(a):
                          "achieved": knn_ach, "peak": peak_gbs, "unit": "GB/s",
                          "frac": (knn_ach / peak_gbs) if knn_ach else None, "traffic": traffic_of("knn_stage"),
                          "algorithmic_bytes_per_launch": knn_bytes, "kernel_ms": k_ms, "peak_source": peak_src,
+                         "isolated": {"kernel_ms": k_iso, "achieved": knn_iso_ach, "frac": (knn_iso_ach / peak_gbs) if knn_iso_ach else None,
+                                      "note": "same segment, one batch at a time, after the timed region"},
                          "note": "exact k-NN on an L1/L2-resident cloud: bound by instruction issue and cache latency, not by "
                                  "HBM (DESIGN.md 3); kernel time measured with CUDA events while other batches' kernels run"},
             "roofline_pixel": {"kernel": "sd::pixel_label_kernel + pixel_scan_kernel + pixel_scatter_kernel", "bound": "hbm",
                                "achieved": pix_ach, "peak": peak_gbs, "unit": "GB/s",
                                "frac": (pix_ach / peak_gbs) if pix_ach else None, "traffic": traffic_of("pixel_stage"),
                                "algorithmic_bytes_per_launch": pix_bytes, "kernel_ms": pix_ms,
+                               "isolated": {"kernel_ms": p_iso, "achieved": pix_iso_ach, "frac": (pix_iso_ach / peak_gbs) if pix_iso_ach else None,
+                                            "note": "same segment, one batch at a time, after the timed region"},
                                "note": "pixel stage (3 kernels) timed as one segment, concurrently with other batches"},
             "roofline_path": {"bound": "hbm", "algorithmic_bytes_per_frame": alg_path,
                               "achieved": alg_path * value / world / 1e9, "peak": peak_gbs, "unit": "GB/s",

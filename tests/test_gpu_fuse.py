@@ -168,3 +168,29 @@ def test_fused_edge_cases(cuda_device):
             assert np.isnan(res.rw[0]), name
         else:
             assert float(res.rw[0]) == o["rw"], name
+
+
+def test_fused_randomised_sweep(cuda_device):
+    """Randomised shapes / seeds / parameters (seeded): every stage count, index list, rw bit-exact against the oracle.
+    Widths that are not multiples of 8 or 32, odd heights, depths where the slab is sparse, k up to 20, and a batch whose
+    frames differ -- the cases the fixed-size tests above do not visit."""
+    rng = np.random.default_rng(2024)
+    shapes = [(72, 132), (100, 260), (136, 300), (190, 404), (250, 500)]
+    for case in range(10):
+        h, w = shapes[case % len(shapes)]
+        seeds = [int(s) for s in rng.integers(0, 10_000, 2)]
+        P = FusionParams(depth=float(rng.choice([8.0, 10.0, 12.5, 16.0])),
+                         sor_nb_neighbors=int(rng.choice([5, 10, 16, 20])),
+                         sor_std_ratio=float(rng.choice([0.3, 0.5, 1.0])),
+                         ror_nb_points=int(rng.choice([20, 80])), ror_radius=float(rng.choice([0.3, 0.5])),
+                         road_mad_x_thr=float(rng.choice([2.0, 3.0])))
+        frames = [scene.make_frame(h, w, s) for s in seeds]
+        intr = frames[0][2]
+        eng = FusionEngine(h, w, max_frames=2, device=cuda_device)
+        lg = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+        dp = torch.from_numpy(np.stack([f[1] for f in frames])).cuda()
+        res = eng.fuse_frames(lg, dp, intr, P)
+        for f, (logits, disp, _) in enumerate(frames):
+            o = frame_ref.fuse_frame(logits, disp, intr.as_q32(), intr.disparity_mult, P)
+            check_against_oracle(res, f, o, eng)
+        eng.close()

@@ -187,6 +187,13 @@ int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_weights, const
 int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_width, int channels,
                        uint8_t* d_dst, int dst_height, int dst_width, void* stream);
 
+/* the vertex rows of PointCloud2Ply.write_ply (semantic_depth_lib/point_cloud_2_ply.py:62-70),
+ * np.savetxt(f, hstack([points3D, colors]), '%f %f %f %d %d %d'), byte for byte.  d_rgb [n][3] uint8; d_out receives
+ * *h_nbytes bytes of ASCII.  Returns SD_ERR_WORKSPACE with the needed size in *h_nbytes when `capacity` is too small.
+ * Synchronises the stream. */
+int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
+                char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream);
+
 /* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
 /* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
 int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream);

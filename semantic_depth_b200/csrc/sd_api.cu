@@ -396,6 +396,25 @@ extern "C" int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_wei
                            d_fence_src, d_counts, d_labels, d_points, d_disp_pp, d_logits_out, ws, stream);
 }
 
+extern "C" int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
+                           char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream) {
+    int rc = check_n(ws, n); if (rc) return rc;
+    if (!h_nbytes || (n > 0 && (!d_x || !d_y || !d_z || !d_rgb || !d_out))) return fail(SD_ERR_INVALID, "sd_ply_rows: null argument");
+    *h_nbytes = 0ull;
+    if (n == 0) return SD_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    CallScratch* cs = call_scratch(ws);
+    // tile totals / offsets live in the neighbour search's cell_start array (2 * ceil(n / 256) words; free between calls)
+    uint32_t* tiles = reinterpret_cast<uint32_t*>(ws->cell_start);
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(cs->d);
+    rc = sd_launch_ply_rows(d_x, d_y, d_z, d_rgb, n, d_out, capacity, tiles, d_total, st); if (rc) return rc;
+    unsigned long long total = 0ull;
+    rc = download_sync(&total, d_total, 1, ws, st); if (rc) return rc;
+    *h_nbytes = total;
+    if (total > capacity) return fail(SD_ERR_WORKSPACE, "sd_ply_rows: output buffer too small (h_nbytes holds the size needed)");
+    return SD_OK;
+}
+
 extern "C" int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_width, int channels,
                                   uint8_t* d_dst, int dst_height, int dst_width, void* stream) {
     if (!d_src || !d_dst || batch < 1 || src_height < 1 || src_width < 1 || dst_height < 1 || dst_width < 1)

@@ -1,0 +1,47 @@
+"""Pin oracle/ply_ref.py against the reference's own PointCloud2Ply (imported unmodified).  BUILD CONTAINER ONLY.
+
+``python tests/golden/make_golden_ply.py`` writes tests/golden/ply_vectors.npz: seeds + sha256 / length / first rows of the
+file the reference class writes, after asserting byte-equality with the oracle."""
+import hashlib
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, "/root/reference")
+from oracle import ply_ref  # noqa: E402
+
+
+def make_cloud(seed, n, dtype):
+    rng = np.random.default_rng(seed)
+    p = (rng.standard_normal((n, 3)) * np.array([4.0, 1.0, 30.0]) + np.array([0.0, -1.5, -40.0])).astype(np.float32)
+    p[::97, 2] = p[:, 2].min()                      # several rows at the minimum z: the infinity filter drops them all
+    special = np.float32([0.0, -0.0, 1e-7, -4.9999999e-7, 5.0000001e-7, 0.5, 2.5e-6, 123456.789, -1e6, 1.0000005, 9.9999995, 3.4e38, 1e-45])
+    p[1:1 + len(special), 0] = special
+    c = rng.integers(0, 256, (n, 3)).astype(np.uint8)
+    return p.astype(dtype), c
+
+
+def main():
+    from semantic_depth_lib.point_cloud_2_ply import PointCloud2Ply          # the reference's class, unmodified
+    out = {}
+    for i, (n, dtype) in enumerate([(1000, np.float32), (50_000, np.float32), (3000, np.float64), (20, np.float32)]):
+        p, c = make_cloud(i, n, dtype)
+        with tempfile.TemporaryDirectory() as d:
+            w = PointCloud2Ply(p.copy(), c.copy(), os.path.join(d, "cloud"))
+            w.prepare_and_save_point_cloud()
+            ref = open(os.path.join(d, "cloud.ply"), "rb").read()
+        mine = ply_ref.prepare_and_save_bytes(p, c)
+        assert mine == ref, (i, len(mine), len(ref))
+        out[f"case{i}"] = np.array([i, n, 1 if dtype == np.float64 else 0, len(ref)])
+        out[f"case{i}_sha256"] = np.frombuffer(hashlib.sha256(ref).digest(), dtype=np.uint8)
+        out[f"case{i}_head"] = np.frombuffer(ref[:400], dtype=np.uint8)
+        print(f"case {i}: {n} points {dtype.__name__} -> {len(ref)} bytes, oracle == reference")
+    np.savez_compressed(os.path.join(HERE, "ply_vectors.npz"), **out)
+
+
+if __name__ == "__main__":
+    main()

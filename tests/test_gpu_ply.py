@@ -1,0 +1,45 @@
+"""GPU PLY writer against the oracle restatement of PointCloud2Ply and the golden digests of the
+files the reference's own class wrote (tests/golden/make_golden_ply.py)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ply_ref
+from semantic_depth_lib.point_cloud_2_ply import PointCloud2Ply
+
+pytestmark = pytest.mark.gpu
+
+
+def test_ply_files_byte_identical(cuda_device, golden_dir, tmp_path):
+    sys.path.insert(0, golden_dir)
+    from make_golden_ply import make_cloud
+    z = np.load(os.path.join(golden_dir, "ply_vectors.npz"))
+    ncases = len([k for k in z.files if k.endswith("_sha256")])
+    assert ncases >= 4
+    for i in range(ncases):
+        seed, n, is64, nbytes = (int(v) for v in z[f"case{i}"])
+        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32)
+        w = PointCloud2Ply(p.copy(), c.copy(), str(tmp_path / f"cloud{i}"))
+        w.prepare_and_save_point_cloud()
+        got = open(tmp_path / f"cloud{i}.ply", "rb").read()
+        assert got == ply_ref.prepare_and_save_bytes(p, c), i
+        assert len(got) == nbytes and hashlib.sha256(got).digest() == z[f"case{i}_sha256"].tobytes()
+        assert got[:400] == z[f"case{i}_head"].tobytes()
+
+
+def test_ply_special_values_and_extra_cloud(cuda_device, tmp_path):
+    vals = np.float32([0.0, -0.0, 0.5, 1.5, 2.5e-6, 3.5e-6, 4.9999999e-7, 5.0000001e-7, -5e-7, 1e-45, 0.9999995, 0.99999994,
+                       123456.7890625, -1e6, 16777216.0, 1e10, 3.4028235e38, -3.4028235e38, 1.17549435e-38, 1234.5678,
+                       np.inf, -np.inf, np.nan, 7.0000005])
+    p = np.stack([vals, vals[::-1], np.linspace(-5, 5, len(vals), dtype=np.float32)], axis=1)
+    c = (np.arange(len(vals) * 3).reshape(-1, 3) * 7 % 256).astype(np.uint8)
+    w = PointCloud2Ply(p, c, str(tmp_path / "special"))
+    w.write_ply(str(tmp_path / "special.ply"))
+    assert open(tmp_path / "special.ply", "rb").read() == ply_ref.ply_bytes(p, c)
+    extra_p = np.float32([[1, 2, 3], [4, 5, 6]]); extra_c = np.uint8([[9, 99, 199], [0, 10, 255]])
+    w.add_extra_point_cloud(extra_p, extra_c)
+    w.write_ply(str(tmp_path / "special2.ply"))
+    assert open(tmp_path / "special2.ply", "rb").read() == ply_ref.ply_bytes(np.vstack([p, extra_p]), np.vstack([c, extra_c]))

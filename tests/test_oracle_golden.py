@@ -151,3 +151,17 @@ def test_resize_oracle_against_cv2_golden(golden_dir):
         got = frame_ref.resize_cubic_u8(make_image(h, w, c, seed), dw, dh)
         d = np.abs(got.astype(int) - z[f"case{i}_cv2"].astype(int))
         assert got.shape == (dh, dw, c) and d.max() <= 1 and (d > 0).mean() < 0.1
+
+
+def test_ply_oracle_against_reference_digests(golden_dir):
+    """oracle.ply_ref against the digests of the files the reference's own PointCloud2Ply wrote."""
+    import hashlib
+    from oracle import ply_ref
+    sys.path.insert(0, golden_dir)
+    from make_golden_ply import make_cloud
+    z = np.load(os.path.join(golden_dir, "ply_vectors.npz"))
+    for i in range(len([k for k in z.files if k.endswith("_sha256")])):
+        seed, n, is64, nbytes = (int(v) for v in z[f"case{i}"])
+        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32)
+        got = ply_ref.prepare_and_save_bytes(p, c)
+        assert len(got) == nbytes and hashlib.sha256(got).digest() == z[f"case{i}_sha256"].tobytes()

@@ -46,6 +46,23 @@ def main():
     by = img.numel() + 8 * 256 * 512 * 3
     out.append({"config": "8f-1: cv2.INTER_CUBIC 8 x 1024x2048x3 -> 256x512x3", "ms": ms, "frames_per_s": 8 / (ms * 1e-3),
                 "gb_per_s": by / (ms * 1e-3) / 1e9})
+    # 8f-3: ASCII PLY rows of a 1 M-point cloud ('%f %f %f %d %d %d'), device formatting only (no file write)
+    import ctypes as C
+    from semantic_depth_b200 import _lib
+    npts = 1_000_000
+    cloud = torch.from_numpy(scene.make_road_cloud(npts, seed=2)).cuda()
+    px, py, pz = (cloud[:, i].contiguous() for i in range(3))
+    rgb = torch.randint(0, 256, (npts, 3), dtype=torch.uint8, device="cuda")
+    engp = engine_for(npts)
+    buf = torch.empty(48 * npts, dtype=torch.uint8, device="cuda")
+    nb = C.c_ulonglong(0)
+    lib = _lib.load()
+    def fmt():
+        lib.sd_ply_rows(px.data_ptr(), py.data_ptr(), pz.data_ptr(), rgb.data_ptr(), npts, buf.data_ptr(), buf.numel(), C.byref(nb),
+                        engp._ws, torch.cuda.current_stream().cuda_stream)
+    ms = timed(fmt, 10)
+    out.append({"config": "8f-3: ASCII PLY rows of 1 M points (np.savetxt '%f %f %f %d %d %d'), device side incl. one host sync",
+                "ms": ms, "rows_per_s": npts / (ms * 1e-3), "output_mb": nb.value / 1e6, "gb_per_s_out": nb.value / (ms * 1e-3) / 1e9})
     for o in out:
         print(json.dumps(o))
 

@@ -298,8 +298,8 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     const char* e = getenv("SD_FUSE_SINGLE_STREAM");
     pv->single_stream = (e && e[0] == '1');
     const char* cs = getenv("SD_KNN_CELL_SCALE");
-    pv->cell_scale = cs ? atof(cs) : 0.6;
-    if (!(pv->cell_scale > 0.0)) pv->cell_scale = 0.6;
+    pv->cell_scale = cs ? atof(cs) : 0.8;
+    if (!(pv->cell_scale > 0.0)) pv->cell_scale = 0.8;
     ws->fused_ready = false;
     *out = ws;
     return SD_OK;

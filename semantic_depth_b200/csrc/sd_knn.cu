@@ -320,7 +320,7 @@ __device__ __noinline__ double knn_exact_sum(const KnnJob& J, const GridRt& g, f
 // candidate, whatever grid row it comes from), so lanes of a warp stay busy until the lane with the most
 // candidates is done.
 // Level:   the finest grid level whose 3x3 cells around the query hold at least 2k points.
-// Phase 1 (bound): up to 2k+14 of those points -- a window of the level's sorted copy in the query's row and
+// Phase 1 (bound): up to 2k+48 of those points -- a window of the level's sorted copy in the query's row and
 //          one in each adjacent row -- go through a branch-free sorted-insertion network on fp32 keys.  The
 //          k-th smallest key U of ANY k-subset of the cloud is an upper bound of the true k-th squared
 //          distance.  (Fewer than 2k points even at the coarsest level: rings of coarse cells grow.)
@@ -340,10 +340,16 @@ constexpr int kSlotBits = 7;
 constexpr int kMaxRows = 8;            // row runs staged per query; wider discs use the nested sweep
 
 template <int K> struct KnnCfg {
-    static constexpr int own_win = K + 4;                                 // phase-1 window in the query's own row
-    static constexpr int side_win = K / 2 + 5;                            // ... in each adjacent row
+#ifndef SD_KNN_OWN
+#define SD_KNN_OWN 16
+#endif
+#ifndef SD_KNN_SIDE
+#define SD_KNN_SIDE 16
+#endif
+    static constexpr int own_win = K + SD_KNN_OWN;                        // phase-1 window in the query's own row
+    static constexpr int side_win = K / 2 + SD_KNN_SIDE;                  // ... in each adjacent row
     static constexpr int min_fed = K + 2;                                 // fewer points than this in the 3x3 cells: coarser level
-    static constexpr int feed_all = 2 * K + 14;                           // up to this many points in the 3x3 cells: all of them are fed
+    static constexpr int feed_all = own_win + 2 * side_win;               // up to this many points in the 3x3 cells: all of them are fed
     static constexpr int feed_cap = 4 * K + 24;                           // ... ring mode
     static constexpr int list_raw = 3 * K + 10;
     static constexpr int list_cap = list_raw > 126 ? 126 : list_raw;      // phase-2 list entries per query (smem, 7-bit slots)

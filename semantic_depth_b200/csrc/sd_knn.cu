@@ -337,7 +337,11 @@ __device__ __noinline__ double knn_exact_sum(const KnnJob& J, const GridRt& g, f
 // A query whose list still overflows after three tightenings (massive ties) is redone by the fp64 slow path.
 constexpr float kKeyErr = 1.5e-6f;     // relative error bound of the fp32 squared distance
 constexpr int kSlotBits = 7;
-constexpr int kMaxRows = 8;            // row runs staged per query; wider discs use the nested sweep
+#ifndef SD_KNN_ROWCELLS
+#define SD_KNN_ROWCELLS 3
+#endif
+constexpr int kRowCells = SD_KNN_ROWCELLS;   // sweep level: the finest one on which the disc radius is below this many cells
+constexpr int kMaxRows = 2 * (kRowCells + 1) + 2;   // row runs staged per query; wider discs go to the heavy kernel
 
 template <int K> struct KnnCfg {
 #ifndef SD_KNN_OWN
@@ -594,7 +598,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 // sweep level: the finest one on which the disc spans at most 7 rows
                 int Ls = kLevels - 1;
 #pragma unroll
-                for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(3 << (2 * l))) Ls = l;
+                for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(kRowCells << (2 * l))) Ls = l;
                 const LevelRt lv = level_of(J, g, Ls);
                 const int k1 = c1 >> lv.shift;
                 const int R = (int)(rad * lv.inv_cell) + 1;
@@ -771,7 +775,7 @@ __device__ __forceinline__ void heavy_for_cells(const KnnJob& J, const GridRt& g
         // small disc (under 1.5 level-1 cells): one run per grid row on the finest level where it spans at most 7 rows
         int Ls = kLevels - 1;
 #pragma unroll
-        for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(3 << (2 * l))) Ls = l;
+        for (int l = kLevels - 2; l >= 0; --l) if (rad * g.inv_cell < (double)(kRowCells << (2 * l))) Ls = l;
         const LevelRt lv = level_of(J, g, Ls);
         const int k1 = cell_coord(h1, g.o1, g.inv_cell, g.d1[0]) >> lv.shift;
         const int R = (int)(rad * lv.inv_cell) + 1;

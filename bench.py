@@ -177,8 +177,10 @@ def run_b200(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-            os.environ["NCCL_DEBUG"] = "WARN"            # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL writes its banner / debug output to stdout by default
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN", ""):
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
     H, W, B, HW = a.height, a.width, a.frames, a.height * a.width
     P = FusionParams()

@@ -944,10 +944,14 @@ sor_mark_kernel(const KnnJob* __restrict__ jobs) {
     const double thr = sor ? J.stats[2] : 0.0;
     const float finf = __int_as_float(0x7f800000);
     int alive_local = 0;
-    for (int p0 = blockIdx.x * kGridThreads; p0 < kLevels * n; p0 += gridDim.x * kGridThreads) {   // warp-uniform trip count
+    // levels the radius search will read: 0, 1 (whole-cell shortcut) and the coarser ones only when it counts there
+    int nlev = 2;
+#pragma unroll
+    for (int l = 2; l < kLevels; ++l) if (g.cell * (double)(1 << (2 * l)) <= 0.25 * J.radius) nlev = l + 1;
+    for (int p0 = blockIdx.x * kGridThreads; p0 < nlev * n; p0 += gridDim.x * kGridThreads) {   // warp-uniform trip count
         const int p = p0 + threadIdx.x;
         bool alive = false; float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < kLevels * n) {
+        if (p < nlev * n) {
             q = J.sp[p];
             alive = true;
             if (sor) {

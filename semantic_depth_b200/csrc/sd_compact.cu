@@ -83,7 +83,7 @@ __device__ __forceinline__ bool eval_pred(const PredRt& p, float x, float y, flo
 // 128-bit loads (x, y, z and the source index), evaluates the predicate, the block scans the keep counts,
 // one warp chains the tile to its predecessors (decoupled look-back), the survivors are staged in shared
 // memory in output order and leave through fully coalesced stores.
-__global__ void __launch_bounds__(kCompactThreads, 4)
+__global__ void __launch_bounds__(kCompactThreads, SD_COMPACT_MINB)
 compact_kernel(const CompactJob* __restrict__ jobs) {
     __shared__ int s_scan[33];
     __shared__ int s_tile;
@@ -347,7 +347,7 @@ int sd_launch_compact(const sd::CompactJob* d_jobs, int njobs, int cap, cudaStre
     using namespace sd;
     if (njobs <= 0) return SD_OK;
     int tiles = max(1, ceil_div(cap, kCompactTile));
-    int target = max(1, (148 * 4) / njobs);           // every job's CTAs are resident together (4 CTAs per SM)
+    int target = max(1, (148 * SD_COMPACT_MINB) / njobs);           // every job's CTAs are resident together
     dim3 grid(min(tiles, target), njobs);
     compact_kernel<<<grid, kCompactThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();

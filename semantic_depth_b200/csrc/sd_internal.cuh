@@ -9,7 +9,13 @@ namespace sd {
 constexpr int kSelBits0 = 11, kSelBits1 = 11, kSelBits2 = 10;   // radix-select digit widths (32 bits)
 constexpr int kSelBins = 2048;
 constexpr int kCompactThreads = 256;
-constexpr int kCompactItems = 8;
+#ifndef SD_COMPACT_ITEMS
+#define SD_COMPACT_ITEMS 8
+#endif
+#ifndef SD_COMPACT_MINB
+#define SD_COMPACT_MINB 4
+#endif
+constexpr int kCompactItems = SD_COMPACT_ITEMS;
 constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 2048 points per tile
 constexpr int kScanTile = 4096;                                 // cell-count scan tile
 constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job

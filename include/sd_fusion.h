@@ -194,6 +194,14 @@ int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_
 int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
                 char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream);
 
+/* SURVEY.md 8f rank 4 (mask paste): the overlaid frame SegmentFrame.segment_frame returns (semantic_depth.py:547-568):
+ * toimage(np.dot(mask, [[r, g, b, a]]), mode="RGBA") pasted with itself as the mask, road first, then fence.
+ * d_frame / d_out [B][H][W][3] uint8 (may alias), d_labels [B][H*W] uint8 (bit0 road, bit1 fence: the pixel stage's
+ * d_labels), road_rgba / fence_rgba 4 host ints in [0, 255] (reference: {128, 64, 128, 64} and {160, 10, 10, 64}),
+ * d_scratch 2*B int32 of device memory owned by the caller.  Never synchronises. */
+int sd_overlay_masks(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int height, int width,
+                     const int32_t* road_rgba, const int32_t* fence_rgba, uint8_t* d_out, int32_t* d_scratch, void* stream);
+
 /* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
 /* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
 int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream);

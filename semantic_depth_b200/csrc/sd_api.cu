@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <string>
 #include <vector>
+#include <algorithm>
 #include <new>
 #include "sd_internal.cuh"
 
@@ -421,6 +422,38 @@ extern "C" int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_heigh
         return fail(SD_ERR_INVALID, "sd_resize_cubic_u8: bad argument");
     if (channels != 1 && channels != 3 && channels != 4) return fail(SD_ERR_UNSUPPORTED, "sd_resize_cubic_u8: channels must be 1, 3 or 4");
     return sd_launch_resize_cubic_u8(d_src, batch, src_height, src_width, channels, d_dst, dst_height, dst_width, (cudaStream_t)stream);
+}
+
+// scipy 1.2.1 bytescale of the int64 layer `mask x rgba` (values {0} U rgba when the mask is partial, rgba when it is
+// full), evaluated like NumPy: int64 difference, fp64 scale, clip, + 0.5, truncation to uint8
+static uint32_t overlay_layer(const int32_t* rgba, bool full) {
+    long long cmin = full ? rgba[0] : 0, cmax = full ? rgba[0] : 0;
+    for (int k = 0; k < 4; ++k) { cmin = std::min<long long>(cmin, rgba[k]); cmax = std::max<long long>(cmax, rgba[k]); }
+    long long cscale = cmax - cmin;
+    if (cscale == 0) cscale = 1;
+    const double scale = 255.0 / (double)cscale;
+    uint32_t packed = 0;
+    for (int k = 0; k < 4; ++k) {
+        double v = (double)((long long)rgba[k] - cmin) * scale + 0.0;
+        v = std::min(std::max(v, 0.0), 255.0) + 0.5;
+        packed |= ((uint32_t)(long long)v & 255u) << (8 * k);
+    }
+    return packed;
+}
+
+extern "C" int sd_overlay_masks(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int height, int width,
+                                const int32_t* road_rgba, const int32_t* fence_rgba, uint8_t* d_out, int32_t* d_scratch,
+                                void* stream) {
+    if (!d_frame || !d_labels || !d_out || !d_scratch || !road_rgba || !fence_rgba || batch < 1 || height < 1 || width < 1)
+        return fail(SD_ERR_INVALID, "sd_overlay_masks: bad argument");
+    if ((long long)height * width > 0x7fffffffll / 4) return fail(SD_ERR_INVALID, "sd_overlay_masks: frame too large");
+    for (int k = 0; k < 4; ++k)
+        if (road_rgba[k] < 0 || road_rgba[k] > 255 || fence_rgba[k] < 0 || fence_rgba[k] > 255)
+            return fail(SD_ERR_INVALID, "sd_overlay_masks: colour components must be in [0, 255]");
+    sd::OverlayLayers L;
+    L.road_partial = overlay_layer(road_rgba, false);  L.road_full = overlay_layer(road_rgba, true);
+    L.fence_partial = overlay_layer(fence_rgba, false); L.fence_full = overlay_layer(fence_rgba, true);
+    return sd_launch_overlay(d_frame, d_labels, batch, height * width, L, d_scratch, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream) {

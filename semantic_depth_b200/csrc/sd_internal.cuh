@@ -179,6 +179,10 @@ struct FinalJob {
 // points inside a cell.  Summing 2^-70 fixed-point images of the values in 128-bit integers is exact
 // and associative, so the cloud mean / std are deterministic run to run (and closer to the real sum
 // than any fp64 summation order).
+// RGBA bytes (little-endian packed) of the pasted segmentation layers after scipy's bytescale, for a mask that covers
+// part of / all of the frame (sd_overlay.cu)
+struct OverlayLayers { uint32_t road_partial, road_full, fence_partial, fence_full; };
+
 struct U128 { unsigned long long lo, hi; };
 __device__ __forceinline__ U128 to_fixed70(double v) {      // floor(v * 2^70) for finite v > 0, else 0
     U128 r{0ull, 0ull};
@@ -273,6 +277,8 @@ int sd_launch_ply_rows(const float* d_x, const float* d_y, const float* d_z, con
                        unsigned long long capacity, uint32_t* d_tile_scratch, unsigned long long* d_total, cudaStream_t st);
 int sd_launch_resize_cubic_u8(const uint8_t* d_src, int batch, int src_h, int src_w, int channels, uint8_t* d_dst, int dst_h, int dst_w,
                               cudaStream_t st);
+int sd_launch_overlay(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int hw, const sd::OverlayLayers& layers,
+                      int* d_counts, uint8_t* d_out, cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
 int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,

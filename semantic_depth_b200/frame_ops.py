@@ -74,6 +74,64 @@ def resize_cubic(frame, size):
     return _back(out, was_torch)
 
 
+ROAD_RGBA = (128, 64, 128, 64)      # semantic_depth.py:556
+FENCE_RGBA = (160, 10, 10, 64)      # semantic_depth.py:564
+
+
+def _overlay_labels(frames_u8, labels_u8, road_rgba, fence_rgba):
+    """frames [B,H,W,3] uint8 and label bytes [B,H*W] (bit0 road, bit1 fence), both on the device -> overlaid frames."""
+    import ctypes as C
+    from . import _lib
+    from ._lib import check
+    b, h, w, _ = frames_u8.shape
+    out = torch.empty_like(frames_u8)
+    scratch = torch.empty(2 * b, dtype=torch.int32, device=frames_u8.device)
+    rc_, fc_ = (C.c_int32 * 4)(*[int(v) for v in road_rgba]), (C.c_int32 * 4)(*[int(v) for v in fence_rgba])
+    with torch.cuda.device(frames_u8.device):
+        check(_lib.load().sd_overlay_masks(frames_u8.data_ptr(), labels_u8.data_ptr(), b, h, w, rc_, fc_, out.data_ptr(),
+                                           scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), "sd_overlay_masks")
+    return out
+
+
+def overlay_masks(frame, road_mask, fence_mask, road_rgba=ROAD_RGBA, fence_rgba=FENCE_RGBA):
+    """The overlaid frame of ``SegmentFrame.segment_frame`` (semantic_depth.py:547-568): the road mask, then the fence
+    mask, pasted as ``toimage(np.dot(mask, [rgba]), mode='RGBA')`` layers with themselves as the paste mask (scipy
+    1.2.1 bytescale + PIL paste arithmetic).  frame [H,W,3] or [B,H,W,3] uint8; masks bool [H,W] / [H,W,1] (or batched)."""
+    was_torch = isinstance(frame, torch.Tensor)
+    t = (frame if was_torch else torch.from_numpy(np.ascontiguousarray(frame)))
+    if t.dtype != torch.uint8 or t.ndim not in (3, 4) or t.shape[-1] != 3:
+        raise ValueError("frame must be uint8 [H,W,3] or [B,H,W,3]")
+    t = t.to(device="cuda").contiguous()
+    batched = t.ndim == 4
+    if not batched:
+        t = t[None]
+    b, h, w, _ = t.shape
+    rm = _dev(road_mask, torch.bool)[0].reshape(b, h * w)
+    fm = _dev(fence_mask, torch.bool)[0].reshape(b, h * w)
+    labels = (rm.to(torch.uint8) | (fm.to(torch.uint8) << 1)).contiguous()
+    out = _overlay_labels(t, labels, road_rgba, fence_rgba)
+    return _back(out if batched else out[0], was_torch)
+
+
+def segment_frame(frame, logits, prob_thr: float = 0.5):
+    """What ``SegmentFrame.segment_frame`` returns after the session run (semantic_depth.py:553-570), from the
+    network's logits [H*W,3]: ``(segmentation_road [H,W,1] bool, segmentation_fence [H,W,1] bool, overlaid [H,W,3] uint8)``.
+    The label bytes of the pixel stage feed the overlay kernel directly."""
+    was_torch = isinstance(frame, torch.Tensor)
+    t = (frame if was_torch else torch.from_numpy(np.ascontiguousarray(frame)))
+    if t.dtype != torch.uint8 or t.ndim != 3 or t.shape[-1] != 3:
+        raise ValueError("frame must be uint8 [H,W,3]")
+    t = t.to(device="cuda").contiguous()
+    h, w, _ = t.shape
+    lg = _dev(logits)[0].reshape(1, h * w, 3)
+    eng = frame_engine(h, w)
+    disp = torch.ones((1, 2, h, w), dtype=torch.float32, device=lg.device)
+    lab = eng.pixel_stage(lg, disp, Intrinsics.synthetic(w), prob_thr=prob_thr)["labels"].reshape(1, h * w).contiguous()
+    out = _overlay_labels(t[None], lab, ROAD_RGBA, FENCE_RGBA)[0]
+    lab = lab.reshape(h, w, 1)
+    return _back((lab & 1) != 0, was_torch), _back((lab & 2) != 0, was_torch), _back(out, was_torch)
+
+
 def upsample_scores(scores, weights, bias):
     """FCN-8s' last layer, ``conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same')`` (fcn8s/fcn.py:207-213):
     scores [h,w,3] -> logits [8h*8w, 3] fp32, evaluated by the label kernel (fp32, fixed summation order)."""

@@ -11,6 +11,7 @@ and the reference lines each function follows.  Additive entry points cover what
 * ``reproject_to_3d``         -- DepthFrame.compute_3D_points (cv2.reprojectImageTo3D), :686-697
 * ``fuse_frames``             -- the whole fusion section of process_frame, :183-324, batched
 * ``resize_cubic``            -- cv2.resize(..., INTER_CUBIC) of the input frame, semantic_depth.py:110-112
+* ``overlay_masks`` / ``segment_frame`` -- the masks and the overlaid frame of SegmentFrame.segment_frame, :547-570
 * ``upsample_scores`` / ``fuse_frames_from_scores`` -- the same path fed by FCN-8s' unexpanded head
   (``second_skip`` + the last transposed convolution, fcn8s/fcn.py:207-213)
 """
@@ -22,4 +23,5 @@ from semantic_depth_b200.pcl_gpu import (  # noqa: F401
 )
 from semantic_depth_b200.frame_ops import (  # noqa: F401
     labels_from_logits, post_process_disparity, reproject_to_3d, fuse_frames, upsample_scores, fuse_frames_from_scores, resize_cubic,
+    overlay_masks, segment_frame,
 )

@@ -165,3 +165,21 @@ def test_ply_oracle_against_reference_digests(golden_dir):
         p, c = make_cloud(seed, n, np.float64 if is64 else np.float32)
         got = ply_ref.prepare_and_save_bytes(p, c)
         assert len(got) == nbytes and hashlib.sha256(got).digest() == z[f"case{i}_sha256"].tobytes()
+
+
+def test_overlay_oracle_against_pil_golden(golden_dir):
+    """oracle.overlay_ref against frames PIL's own Image.paste produced (make_golden_overlay.py)."""
+    from oracle import overlay_ref
+    z = np.load(os.path.join(golden_dir, "overlay_vectors.npz"))
+    n = len([k for k in z.files if k.endswith("_out")])
+    assert n >= 7
+    for i in range(n):
+        got = overlay_ref.overlay_from_labels(z[f"case{i}_frame"], z[f"case{i}_labels"],
+                                              tuple(z[f"case{i}_road_rgba"]), tuple(z[f"case{i}_fence_rgba"]))
+        assert np.array_equal(got, z[f"case{i}_out"]), i
+    # the bytescale corner cases the layer constants come from
+    assert overlay_ref.mask_rgba(np.array([[True, False]]), overlay_ref.ROAD_RGBA)[0, 0].tolist() == [255, 128, 255, 128]
+    assert overlay_ref.mask_rgba(np.array([[True, False]]), overlay_ref.FENCE_RGBA)[0, 0].tolist() == [255, 16, 16, 102]
+    assert overlay_ref.mask_rgba(np.array([[True, True]]), overlay_ref.ROAD_RGBA)[0, 0].tolist() == [255, 0, 255, 0]
+    assert overlay_ref.mask_rgba(np.array([[True, True]]), overlay_ref.FENCE_RGBA)[0, 0].tolist() == [255, 0, 0, 92]
+    assert not overlay_ref.mask_rgba(np.array([[False, False]]), overlay_ref.ROAD_RGBA).any()

@@ -193,6 +193,10 @@ int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_
  * Synchronises the stream. */
 int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
                 char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream);
+/* The same for float64 clouds (the reference's clouds are float64 after the Open3D round trip, semantic_depth.py:244,
+ * and its plane meshes / lines are float64 throughout, pcl.py:107-113,321-331).  Finite |values| must be < 2^128. */
+int sd_ply_rows_f64(const double* d_x, const double* d_y, const double* d_z, const uint8_t* d_rgb, int n,
+                    char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream);
 
 /* SURVEY.md 8f rank 4 (mask paste): the overlaid frame SegmentFrame.segment_frame returns (semantic_depth.py:547-568):
  * toimage(np.dot(mask, [[r, g, b, a]]), mode="RGBA") pasted with itself as the mask, road first, then fence.

@@ -397,8 +397,9 @@ extern "C" int sd_pixel_fuse_scores(const float* d_scores, const float* d_up_wei
                            d_fence_src, d_counts, d_labels, d_points, d_disp_pp, d_logits_out, ws, stream);
 }
 
-extern "C" int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
-                           char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream) {
+template <typename T, typename Launch>
+static int ply_rows_impl(const T* d_x, const T* d_y, const T* d_z, const uint8_t* d_rgb, int n, char* d_out,
+                         unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream, Launch launch) {
     int rc = check_n(ws, n); if (rc) return rc;
     if (!h_nbytes || (n > 0 && (!d_x || !d_y || !d_z || !d_rgb || !d_out))) return fail(SD_ERR_INVALID, "sd_ply_rows: null argument");
     *h_nbytes = 0ull;
@@ -408,12 +409,22 @@ extern "C" int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z,
     // tile totals / offsets live in the neighbour search's cell_start array (2 * ceil(n / 256) words; free between calls)
     uint32_t* tiles = reinterpret_cast<uint32_t*>(ws->cell_start);
     unsigned long long* d_total = reinterpret_cast<unsigned long long*>(cs->d);
-    rc = sd_launch_ply_rows(d_x, d_y, d_z, d_rgb, n, d_out, capacity, tiles, d_total, st); if (rc) return rc;
+    rc = launch(d_x, d_y, d_z, d_rgb, n, d_out, capacity, tiles, d_total, st); if (rc) return rc;
     unsigned long long total = 0ull;
     rc = download_sync(&total, d_total, 1, ws, st); if (rc) return rc;
     *h_nbytes = total;
     if (total > capacity) return fail(SD_ERR_WORKSPACE, "sd_ply_rows: output buffer too small (h_nbytes holds the size needed)");
     return SD_OK;
+}
+
+extern "C" int sd_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n,
+                           char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream) {
+    return ply_rows_impl(d_x, d_y, d_z, d_rgb, n, d_out, capacity, h_nbytes, ws, stream, sd_launch_ply_rows);
+}
+
+extern "C" int sd_ply_rows_f64(const double* d_x, const double* d_y, const double* d_z, const uint8_t* d_rgb, int n,
+                               char* d_out, unsigned long long capacity, unsigned long long* h_nbytes, SdWorkspace* ws, void* stream) {
+    return ply_rows_impl(d_x, d_y, d_z, d_rgb, n, d_out, capacity, h_nbytes, ws, stream, sd_launch_ply_rows_f64);
 }
 
 extern "C" int sd_resize_cubic_u8(const uint8_t* d_src, int batch, int src_height, int src_width, int channels,

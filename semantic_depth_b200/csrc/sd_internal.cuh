@@ -275,6 +275,8 @@ int sd_launch_cell_box_init(uint4* d_box, size_t count, cudaStream_t st);
 int sd_launch_ybox_init(uint2* d_box, size_t count, cudaStream_t st);
 int sd_launch_ply_rows(const float* d_x, const float* d_y, const float* d_z, const uint8_t* d_rgb, int n, char* d_out,
                        unsigned long long capacity, uint32_t* d_tile_scratch, unsigned long long* d_total, cudaStream_t st);
+int sd_launch_ply_rows_f64(const double* d_x, const double* d_y, const double* d_z, const uint8_t* d_rgb, int n, char* d_out,
+                           unsigned long long capacity, uint32_t* d_tile_scratch, unsigned long long* d_total, cudaStream_t st);
 int sd_launch_resize_cubic_u8(const uint8_t* d_src, int batch, int src_h, int src_w, int channels, uint8_t* d_dst, int dst_h, int dst_w,
                               cudaStream_t st);
 int sd_launch_overlay(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int hw, const sd::OverlayLayers& layers,

@@ -45,10 +45,14 @@ class PointCloud2Ply():
     def _device_cloud(points3D, colors):
         p = np.ascontiguousarray(points3D)
         if p.dtype == np.float64:
-            p32 = p.astype(np.float32)
-            if not np.array_equal(p32.astype(np.float64), p, equal_nan=True):
-                raise NotImplementedError("float64 cloud is not exactly representable in float32")
-            p = p32
+            with np.errstate(over="ignore"):
+                p32 = p.astype(np.float32)
+            if np.array_equal(p32.astype(np.float64), p, equal_nan=True):
+                p = p32                                # e.g. a cloud that only made the Open3D round trip (semantic_depth.py:244)
+            else:                                      # plane meshes, lines (pcl.py:107-113,321-331): formatted as float64
+                fin = np.abs(p[np.isfinite(p)])
+                if fin.size and fin.max() >= 2.0 ** 128:
+                    raise NotImplementedError("finite float64 coordinates must be below 2^128")
         elif p.dtype != np.float32:
             raise TypeError("points3D must be float32 or float64")
         c = np.asarray(colors)
@@ -71,7 +75,8 @@ class PointCloud2Ply():
         for _ in range(2):
             out = torch.empty(capacity, dtype=torch.uint8, device=x.device)
             nbytes = C.c_ulonglong(0)
-            rc = lib.sd_ply_rows(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), n, out.data_ptr(), capacity,
+            fn = lib.sd_ply_rows if x.dtype == torch.float32 else lib.sd_ply_rows_f64
+            rc = fn(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), n, out.data_ptr(), capacity,
                                  C.byref(nbytes), eng._ws, torch.cuda.current_stream().cuda_stream)
             if rc == 0:
                 return out[: nbytes.value].cpu().numpy().tobytes()
@@ -98,12 +103,17 @@ class PointCloud2Ply():
         if n == 0:
             raise ValueError("zero-size array to reduction operation minimum which has no identity")   # np.min of the reference
         x, y, z, _ = self._device_cloud(self.points3D, self.colors)
-        eng = engine_for(n)
-        zmin, _, _ = eng.slab_minmax(z, z, -np.inf, np.inf, use_f32=True)      # min of z over all rows
-        if np.isnan(self.points3D[:, 2]).any():
-            zmin = np.float32(np.nan)                                           # np.min propagates NaN -> nothing is kept
-        keep, _ = eng.filter(x, y, z, SdPredicate(kind=PRED_GT, axis=2, fa=float(zmin)), want_points=False)
-        idx = keep.cpu().numpy().astype(np.int64)
+        if z.dtype == torch.float64:
+            # genuinely float64 rows (visualisation meshes / lines appended to the cloud): the filter kernels work on
+            # float32 columns, so this one predicate is evaluated with torch (same semantics: NaN minimum keeps nothing)
+            idx = torch.nonzero(z > z.min()).reshape(-1).cpu().numpy().astype(np.int64)
+        else:
+            eng = engine_for(n)
+            zmin, _, _ = eng.slab_minmax(z, z, -np.inf, np.inf, use_f32=True)      # min of z over all rows
+            if np.isnan(self.points3D[:, 2]).any():
+                zmin = np.float32(np.nan)                                           # np.min propagates NaN -> nothing is kept
+            keep, _ = eng.filter(x, y, z, SdPredicate(kind=PRED_GT, axis=2, fa=float(zmin)), want_points=False)
+            idx = keep.cpu().numpy().astype(np.int64)
         self.points3D = self.points3D[idx]
         self.colors = self.colors[idx]
         self.write_ply('{}.ply'.format(self.output_name))

@@ -21,7 +21,7 @@ def test_ply_files_byte_identical(cuda_device, golden_dir, tmp_path):
     assert ncases >= 4
     for i in range(ncases):
         seed, n, is64, nbytes = (int(v) for v in z[f"case{i}"])
-        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32)
+        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32, is64 == 2)
         w = PointCloud2Ply(p.copy(), c.copy(), str(tmp_path / f"cloud{i}"))
         w.prepare_and_save_point_cloud()
         got = open(tmp_path / f"cloud{i}.ply", "rb").read()
@@ -43,3 +43,39 @@ def test_ply_special_values_and_extra_cloud(cuda_device, tmp_path):
     w.add_extra_point_cloud(extra_p, extra_c)
     w.write_ply(str(tmp_path / "special2.ply"))
     assert open(tmp_path / "special2.ply", "rb").read() == ply_ref.ply_bytes(np.vstack([p, extra_p]), np.vstack([c, extra_c]))
+
+
+def test_ply_float64_rows(cuda_device, tmp_path):
+    """Genuinely float64 rows (the reference's plane meshes and lines): exact '%f' of a double, every exponent range."""
+    rng = np.random.default_rng(11)
+    bits = rng.integers(0, 2 ** 63, 60_000, dtype=np.int64).astype(np.uint64)
+    expo = rng.integers(1023 - 80, 1023 + 127, 60_000).astype(np.uint64)           # 2^-80 .. 2^127
+    v = ((bits & np.uint64((1 << 52) - 1)) | (expo << np.uint64(52))).view(np.float64)
+    v[::2] *= -1.0
+    v[:8] = [5e-324, 2.2250738585072014e-308, 1e-7, 0.0078125, 0.0234375, 1.7976931348623157e308, np.inf, np.nan]
+    v[5] = 1.5 * 2.0 ** 127
+    p = v.reshape(-1, 3).copy()
+    c = rng.integers(0, 256, p.shape).astype(np.uint8)
+    w = PointCloud2Ply(p, c, str(tmp_path / "f64"))
+    w.write_ply(str(tmp_path / "f64.ply"))
+    assert open(tmp_path / "f64.ply", "rb").read() == ply_ref.ply_bytes(p, c)
+    # values of 2^128 and above are refused loudly
+    p[0, 0] = 2.0 ** 128
+    with pytest.raises(NotImplementedError):
+        PointCloud2Ply(p, c, str(tmp_path / "big")).write_ply(str(tmp_path / "big.ply"))
+
+
+def test_ply_cloud_plus_float64_line(cuda_device, tmp_path):
+    """The reference's dump: a float32-born road cloud with the float64 rw line appended (sequence:372-376)."""
+    import semantic_depth_lib.pcl as pcl
+    rng = np.random.default_rng(2)
+    road = (rng.standard_normal((5000, 3)) * [3.0, 0.05, 20.0] + [0.0, -1.5, -30.0]).astype(np.float32).astype(np.float64)
+    colors = rng.integers(0, 256, road.shape).astype(np.float64)          # colours are float64 after Open3D (:244)
+    left, right = np.array([[-3.7123, -1.52, -9.98]]), np.array([[3.4119, -1.49, -9.97]])
+    line, line_colors = pcl.create_3Dline_from_3Dpoints(left.copy(), right.copy(), [250, 0, 0])
+    line[:, 2] += 0.2
+    w = PointCloud2Ply(road, colors, str(tmp_path / "rw"))
+    w.add_extra_point_cloud(line, line_colors)
+    w.prepare_and_save_point_cloud()
+    want = ply_ref.prepare_and_save_bytes(np.vstack([road, line]), np.vstack([colors, line_colors]))
+    assert open(tmp_path / "rw.ply", "rb").read() == want

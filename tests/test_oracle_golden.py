@@ -162,7 +162,7 @@ def test_ply_oracle_against_reference_digests(golden_dir):
     z = np.load(os.path.join(golden_dir, "ply_vectors.npz"))
     for i in range(len([k for k in z.files if k.endswith("_sha256")])):
         seed, n, is64, nbytes = (int(v) for v in z[f"case{i}"])
-        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32)
+        p, c = make_cloud(seed, n, np.float64 if is64 else np.float32, is64 == 2)
         got = ply_ref.prepare_and_save_bytes(p, c)
         assert len(got) == nbytes and hashlib.sha256(got).digest() == z[f"case{i}_sha256"].tobytes()
 

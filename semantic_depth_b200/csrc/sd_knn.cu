@@ -483,6 +483,9 @@ __device__ __forceinline__ void flush_stats(GridState* gs, U128 acc_sum, U128 ac
 constexpr int kHeavy = SD_KNN_HEAVY;            // a disc with more candidates than this is swept by the whole warp
 constexpr int kExtreme = 4096;                  // ... and beyond this it goes to knn_heavy_kernel (3-D cell pruning, exact re-bounding)
 
+#ifndef SD_KNN_WAVES
+#define SD_KNN_WAVES 16     // CTAs launched per SM (4 are resident; CTAs claim work until the queue is empty)
+#endif
 #ifndef SD_KNN_MINB
 #define SD_KNN_MINB 4
 #endif
@@ -1159,7 +1162,7 @@ int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStrea
     using namespace sd;
     if (njobs <= 0) return SD_OK;
     if (k < 1 || k > kMaxKnnK) return SD_ERR_INVALID;
-    dim3 grid = grid_for(cap, kKnnThreads, 1, njobs, 16);   // <= kKnnMaxBlocks CTAs per job
+    dim3 grid = grid_for(cap, kKnnThreads, 1, njobs, SD_KNN_WAVES);   // <= kKnnMaxBlocks CTAs per job
     if (k <= 3) return launch_knn_t<4>(d_jobs, grid, st);
     if (k <= 7) return launch_knn_t<8>(d_jobs, grid, st);
     if (k <= 10) return launch_knn_t<11>(d_jobs, grid, st);

@@ -151,3 +151,54 @@ def test_bench_alg_bytes_matches_survey_formula():
               "right_mad_x": 232772, "right_plane": 232772}
     b = bench.b_alg_bytes(counts, 1024 * 2048)
     assert abs(b / 1e6 - 203.9) < 0.5      # 203.9 MB for the seed-0 frame
+
+
+def test_header_is_plain_c_and_layouts_match_field_by_field(tmp_path):
+    """include/sd_fusion.h compiles as C99 (no C++ / CUDA / torch types at the boundary) and every field of every struct
+    sits where the ctypes mirror puts it."""
+    import shutil
+    from semantic_depth_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    structs = {"SdCamera": _lib.SdCamera, "SdParams": _lib.SdParams, "SdFrameResult": _lib.SdFrameResult,
+               "SdPredicate": _lib.SdPredicate}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sd_fusion.h"', "int main(void) {"]
+    for cname, ctype in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ctype._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("SD_NUM_COUNTS %d\\n", (int)SD_NUM_COUNTS);', "  return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, ctype in structs.items():
+        assert int(got[cname]) == C.sizeof(ctype), cname
+        for fname, _ in ctype._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ctype, fname).offset, f"{cname}.{fname}"
+    assert int(got["SD_NUM_COUNTS"]) == _lib.SD_NUM_COUNTS
+
+
+def test_frame_processor_constructor_contract():
+    from semantic_depth_b200.frame_processor import FrameProcessor
+
+    class Seg:
+        def logits(self, frame):
+            return None
+
+    class Dep:
+        def disparities(self, frame):
+            return None
+
+    p = FrameProcessor(Seg(), Dep(), (256, 512), approach="rw", depth=12.5)
+    assert p.params.approach == "rw" and p.params.depth == 12.5 and p.input_shape == (256, 512)
+    assert p._intrinsics(2048).disparity_mult == 2048.0                  # semantic_depth.py:109: the original width
+    assert FrameProcessor(Seg(), Dep(), (256, 512), disp_multiplier=3800)._intrinsics(2048).disparity_mult == 3800.0   # sequence:105
+    with pytest.raises(TypeError):
+        FrameProcessor(object(), Dep(), (256, 512))
+    with pytest.raises(ValueError):
+        FrameProcessor(Seg(), Dep(), (256, 512), approach="f2f")

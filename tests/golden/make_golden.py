@@ -218,9 +218,13 @@ def reference_chain(ref_pcl, post_processing, compute_3D_points, logits, disp, i
             "disparity": disparity, "coeff": {"road": road_coeff, "left": left_coeff, "right": right_coeff}}
 
 
-def check_frames(ref_pcl, post_processing, compute_3D_points):
+FRAME_CASES = ((64, 128, 0), (128, 256, 0), (128, 256, 3), (256, 512, 0), (256, 512, 1), (512, 1024, 0),
+               (1024, 2048, 0))       # the last one is BASELINE.json's full size (about a minute of CPU)
+
+
+def check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES):
     P = FusionParams()
-    for (h, w, seed) in ((64, 128, 0), (128, 256, 0), (128, 256, 3), (256, 512, 0), (256, 512, 1), (512, 1024, 0)):
+    for (h, w, seed) in cases:
         logits, disp, intr = scene.make_frame(h, w, seed)
         ref = reference_chain(ref_pcl, post_processing, compute_3D_points, logits, disp, intr, P)
         # pixel-stage oracle functions against the lifted reference methods
@@ -279,6 +283,9 @@ def check_pixel_vectors(post_processing, compute_3D_points):
 
 def main():
     ref_pcl, post_processing, compute_3D_points = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-full-size":
+        check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES[-1:])
+        return
     rng = np.random.default_rng(20260101)
     vec = check_functions(ref_pcl, rng)
     np.savez_compressed(os.path.join(HERE, "pcl_vectors.npz"), **vec)

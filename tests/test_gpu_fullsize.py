@@ -211,3 +211,27 @@ def test_config5_ransac_sweep_bit_exact(full_frame, K):
         assert torch.equal(got, ref), (stage, K, int((got != ref).sum()))
         allc = counts.cpu().numpy()
         assert best == int(np.argmax(allc))            # lowest index on ties
+
+
+def test_config4_against_oracle_golden(cuda_device, golden_dir):
+    """BASELINE.json configs[3] against the CPU oracle's answers for ALL 2 M points (tests/golden/make_golden_config4.py):
+    the per-point mean distances are bit-identical (SHA-256 of the fp64 array), so are the kept indices."""
+    import hashlib
+    import os
+    g = np.load(os.path.join(golden_dir, "config4_sor.npz"))
+    n, k, ratio, seed = int(g["n"]), int(g["k"]), float(g["ratio"]), int(g["seed"])
+    pts = torch.from_numpy(scene.make_road_cloud(n, seed=seed)).cuda()
+    x, y, z = (pts[:, i].contiguous() for i in range(3))
+    avg, stats = engine_for(n).knn_mean_distance(x, y, z, k, ratio)
+    a = avg.cpu().numpy()
+    assert a.dtype == np.float64 and a.shape == (n,)
+    assert np.array_equal(a[g["sample_idx"]], g["sample_avg"])
+    assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() == g["avg_sha256"].tobytes()
+    # cloud statistics: order-independent exact accumulation here, sequential fp64 sums in the oracle
+    assert abs(stats[0] - float(g["mean"])) <= 1e-12 * float(g["mean"])
+    assert abs(stats[2] - float(g["thr"])) <= 1e-12 * float(g["thr"])
+    assert float(g["tie_margin_rel"]) > 1e-9                       # no point close enough to the threshold to flip
+    keep = np.flatnonzero((a > 0) & (a < stats[2]))
+    assert keep.size == int(g["kept"])
+    chk = int(np.sum(keep.astype(np.uint64) * (np.arange(keep.size, dtype=np.uint64) % 65521 + 1)) % (1 << 63))
+    assert chk == int(g["kept_checksum"])

@@ -147,6 +147,20 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
+def golden_check(h: int, w: int, rw: float, f2f: float, counts: dict):
+    """Frame 0 of rank 0 is the seed-0 frame: compare its answers with the committed fixture that the reference's own
+    pcl.py chain produced (tests/golden/make_golden.py).  Reads a data file only; nothing of oracle/ runs here."""
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", f"frame_{h}x{w}_seed0.npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    bad = [k for k, v in counts.items() if int(g[f"count/{k}"]) != int(v)]
+    return {"fixture": os.path.relpath(path, ROOT), "stage_counts_equal": not bad, "mismatched_stages": bad,
+            "rw_bit_equal": bool(float(g["rw"]) == rw), "f2f_abs_err": abs(float(g["f2f"]) - f2f)}
+
+
+
 def b_alg_bytes(counts: dict, hw: int) -> float:
     """20*H*W + 12*(N_R0+N_F0) + 12*sum_stages(N_in+N_out) + 12*N_slab_in."""
     c = counts
@@ -393,6 +407,7 @@ def run_b200(a):
             "gpu_launches": int(pipe.slots[0].engine.kernel_count(P)) * a.steps,
             "result_mismatches_vs_first_pass": mism,
             "answers_frame0": {"rw": float(expected[0].rw[0]), "f2f": float(expected[0].f2f[0]), "counts": counts0},
+            "golden_check_frame0": golden_check(H, W, float(expected[0].rw[0]), float(expected[0].f2f[0]), counts0),
             "clocks": sampler.summary(),
             "host_wall_ms": wall * 1e3,
             "batch_latency_ms": {"mean": float(np.mean(total_ms)) if total_ms else None,

@@ -12,7 +12,13 @@
 
 namespace sd {
 
-constexpr int kSelThreads = 512;
+#ifndef SD_SEL_THREADS
+#define SD_SEL_THREADS 512
+#endif
+#ifndef SD_SEL_WAVES
+#define SD_SEL_WAVES 2      // CTAs per SM over all jobs of a launch (per pass alone: 1 -> 28 us, 2 -> 18 us, 4 -> 15 us; the pipelined step is the same for 2 and 4)
+#endif
+constexpr int kSelThreads = SD_SEL_THREADS;
 constexpr int kSelItems = 8;
 
 template <int PASS> struct SelPass;
@@ -155,7 +161,7 @@ int sd_launch_select_median(const sd::SelJob* d_jobs, int njobs, int cap, cudaSt
     if (njobs <= 0) return SD_OK;
     const int tile = kSelThreads * kSelItems;
     int per_job = ceil_div(cap, tile);
-    int target = max(1, (148 * 2) / njobs);
+    int target = max(1, (148 * SD_SEL_WAVES) / njobs);
     per_job = max(1, min(per_job, target));
     dim3 grid(per_job, njobs);
     select_pass_kernel<0><<<grid, kSelThreads, 0, st>>>(d_jobs);

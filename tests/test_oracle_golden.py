@@ -183,3 +183,15 @@ def test_overlay_oracle_against_pil_golden(golden_dir):
     assert overlay_ref.mask_rgba(np.array([[True, True]]), overlay_ref.ROAD_RGBA)[0, 0].tolist() == [255, 0, 255, 0]
     assert overlay_ref.mask_rgba(np.array([[True, True]]), overlay_ref.FENCE_RGBA)[0, 0].tolist() == [255, 0, 0, 92]
     assert not overlay_ref.mask_rgba(np.array([[False, False]]), overlay_ref.ROAD_RGBA).any()
+
+
+def test_config4_fixture_reproducible(golden_dir):
+    """BASELINE.json configs[3]: the committed answers of the 2 M-point statistical filter are what the oracle computes."""
+    import hashlib
+    from oracle import frame_ref
+    g = np.load(os.path.join(golden_dir, "config4_sor.npz"))
+    pts = scene.make_road_cloud(int(g["n"]), seed=int(g["seed"]))
+    keep, avg, (thr, mu, sd) = frame_ref.keep_statistical_outlier_removal(pts, int(g["k"]), float(g["ratio"]), workers=-1)
+    assert hashlib.sha256(np.ascontiguousarray(avg).tobytes()).digest() == g["avg_sha256"].tobytes()
+    assert thr == float(g["thr"]) and mu == float(g["mean"]) and sd == float(g["std"])
+    assert keep.size == int(g["kept"]) and np.array_equal(avg[g["sample_idx"]], g["sample_avg"])

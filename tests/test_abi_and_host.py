@@ -215,5 +215,6 @@ def test_bench_reference_arm_prints_one_contract_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "fusion_frames_per_sec_1024x2048" and d["unit"] == "frames/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 2 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and 2 <= d["cpu_baseline"]["cores"] <= os.cpu_count()      # 2 processes x their k-d tree threads
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

@@ -222,7 +222,18 @@ FRAME_CASES = ((64, 128, 0), (128, 256, 0), (128, 256, 3), (256, 512, 0), (256, 
                (1024, 2048, 0))       # the last one is BASELINE.json's full size (about a minute of CPU)
 
 
-def check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES):
+def _store(path, fix, verify):
+    """Write the fixture, or (verify) assert that the committed file holds exactly these arrays."""
+    if not verify:
+        np.savez_compressed(path, **fix)
+        return
+    old = np.load(path)
+    assert set(old.files) == set(fix), (path, set(old.files) ^ set(fix))
+    for k, v in fix.items():
+        assert same(old[k], np.asarray(v)), (path, k)
+
+
+def check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES, verify=False):
     P = FusionParams()
     for (h, w, seed) in cases:
         logits, disp, intr = scene.make_frame(h, w, seed)
@@ -255,7 +266,7 @@ def check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES)
         for which in ("road", "left", "right"):
             c = o["coeff"][which]
             fix[f"coeff/{which}"] = np.float64([c["Cx"], c["Cy"], c["Cz"], c["C"]])
-        np.savez_compressed(os.path.join(HERE, f"frame_{h}x{w}_seed{seed}.npz"), **fix)
+        _store(os.path.join(HERE, f"frame_{h}x{w}_seed{seed}.npz"), fix, verify)
         print(f"frame {h}x{w} seed {seed}: reference == oracle on {len(ref['stages'])} stages; "
               f"rw={o['rw']} f2f={o['f2f']} status={o['status']} counts={dict(o['counts'])}")
 
@@ -286,14 +297,18 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--only-full-size":
         check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES[-1:])
         return
+    # --verify: recompute everything from the live reference and compare with the committed files instead of writing
+    verify = len(sys.argv) > 1 and sys.argv[1] == "--verify"
     rng = np.random.default_rng(20260101)
     vec = check_functions(ref_pcl, rng)
-    np.savez_compressed(os.path.join(HERE, "pcl_vectors.npz"), **vec)
+    _store(os.path.join(HERE, "pcl_vectors.npz"), vec, verify)
     print(f"pcl function vectors: {len(vec)} arrays, reference == oracle")
     pix = check_pixel_vectors(post_processing, compute_3D_points)
-    np.savez_compressed(os.path.join(HERE, "pixel_vectors.npz"), **pix)
+    _store(os.path.join(HERE, "pixel_vectors.npz"), pix, verify)
     print(f"pixel vectors: {len(pix)} arrays, reference (cv2) == oracle")
-    check_frames(ref_pcl, post_processing, compute_3D_points)
+    check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES[:5] if verify else FRAME_CASES, verify=verify)
+    if verify:
+        print("committed fixtures == live reference")
 
 
 if __name__ == "__main__":

@@ -71,7 +71,13 @@ def main():
         out[f"case{i}_frame"], out[f"case{i}_labels"], out[f"case{i}_out"] = frame, labels, ref
         out[f"case{i}_road_rgba"], out[f"case{i}_fence_rgba"] = rc, fc
         print(f"case {i}: {h}x{w}, {int((ref != frame).sum())} bytes changed, oracle == PIL")
-    np.savez_compressed(os.path.join(HERE, "overlay_vectors.npz"), **out)
+    path = os.path.join(HERE, "overlay_vectors.npz")
+    if len(sys.argv) > 1 and sys.argv[1] == "--verify":
+        old = np.load(path)
+        assert set(old.files) == set(out) and all(np.array_equal(old[k], out[k]) for k in out)
+        print("committed fixtures == live reference")
+    else:
+        np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":

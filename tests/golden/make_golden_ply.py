@@ -52,7 +52,13 @@ def main():
         out[f"case{i}_sha256"] = np.frombuffer(hashlib.sha256(ref).digest(), dtype=np.uint8)
         out[f"case{i}_head"] = np.frombuffer(ref[:400], dtype=np.uint8)
         print(f"case {i}: {n} points {dtype.__name__} -> {len(ref)} bytes, oracle == reference")
-    np.savez_compressed(os.path.join(HERE, "ply_vectors.npz"), **out)
+    path = os.path.join(HERE, "ply_vectors.npz")
+    if len(sys.argv) > 1 and sys.argv[1] == "--verify":
+        old = np.load(path)
+        assert set(old.files) == set(out) and all(np.array_equal(old[k], out[k]) for k in out)
+        print("committed fixtures == live reference")
+    else:
+        np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":

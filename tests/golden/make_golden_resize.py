@@ -38,7 +38,13 @@ def main():
         print(f"case {i} {h}x{w}x{c} -> {dh}x{dw}: max |cv2 - fixed point| = {d.max()}, differing {100 * (d > 0).mean():.3f} %")
         out[f"case{i}_shape"] = np.array([h, w, dh, dw, c, i])
         out[f"case{i}_cv2"] = ref
-    np.savez_compressed(os.path.join(HERE, "resize_vectors.npz"), **out)
+    path = os.path.join(HERE, "resize_vectors.npz")
+    if len(sys.argv) > 1 and sys.argv[1] == "--verify":
+        old = np.load(path)
+        assert set(old.files) == set(out) and all(np.array_equal(old[k], out[k]) for k in out)
+        print("committed fixtures == live reference")
+    else:
+        np.savez_compressed(path, **out)
 
 
 if __name__ == "__main__":

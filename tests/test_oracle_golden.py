@@ -195,3 +195,16 @@ def test_config4_fixture_reproducible(golden_dir):
     assert hashlib.sha256(np.ascontiguousarray(avg).tobytes()).digest() == g["avg_sha256"].tobytes()
     assert thr == float(g["thr"]) and mu == float(g["mean"]) and sd == float(g["std"])
     assert keep.size == int(g["kept"]) and np.array_equal(avg[g["sample_idx"]], g["sample_avg"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/semantic_depth_lib"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("script,args", [("make_golden.py", ["--verify"]), ("make_golden_ply.py", ["--verify"]),
+                                         ("make_golden_overlay.py", ["--verify"]), ("make_golden_resize.py", ["--verify"])])
+def test_committed_fixtures_equal_live_reference(golden_dir, script, args):
+    """Build container only: re-run the generators against the reference's own code (its unmodified pcl.py, the
+    DepthFrame methods lifted from semantic_depth.py, its PointCloud2Ply; PIL's paste for the overlay) and compare with the
+    committed fixtures.  A subprocess keeps the reference's `semantic_depth_lib` out of this process."""
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(golden_dir, script), *args], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "committed fixtures == live reference" in out.stdout

@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 40)")
     ap.add_argument("--cpu-procs", type=int, default=0)
     ap.add_argument("--ref-budget-s", type=float, default=240.0)
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to its GPU's NUMA node before pinning host buffers")
     return ap.parse_args()
 
 
@@ -190,6 +191,9 @@ def run_b200(a):
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # host placement BEFORE any pinned allocation: CPUs and memory of the NUMA node this rank's GPU hangs off
+    from semantic_depth_b200 import hostmem
+    binding = {"bound": False} if a.no_bind else hostmem.bind_to_gpu(local_rank)
     if world > 1:
         # keep stdout to the one JSON line: NCCL writes its banner / debug output to stdout by default
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -409,6 +413,7 @@ def run_b200(a):
             "answers_frame0": {"rw": float(expected[0].rw[0]), "f2f": float(expected[0].f2f[0]), "counts": counts0},
             "golden_check_frame0": golden_check(H, W, float(expected[0].rw[0]), float(expected[0].f2f[0]), counts0),
             "clocks": sampler.summary(),
+            "host_binding": {**binding, "pinned_pages_on_node": hostmem.node_histogram(h_logits[0].data_ptr(), h_logits[0].numel() * 4)},
             "host_wall_ms": wall * 1e3,
             "batch_latency_ms": {"mean": float(np.mean(total_ms)) if total_ms else None,
                                  "note": "first to last kernel of one batch, CUDA events, while other batches overlap"},

@@ -249,7 +249,9 @@ int sd_plane_fit(const float* d_x, const float* d_y, const float* d_z, int n, in
 /* np.mean of an fp32 column with NumPy's pairwise fp32 summation order (pcl.py:258). */
 int sd_mean_f32(const float* d_col, int n, float* h_mean, SdWorkspace* ws, void* stream);
 
-/* min / max of x over the points with lo < z < hi and their count (pcl.py:283,307-308). */
+/* min / max of x over the points with lo < z < hi and their count (pcl.py:283,307-308).  use_f32: 0 = fp64 bounds,
+ * 1 = bounds rounded to fp32 (NumPy's rule for an fp32 cloud), 2 = no slab test: every row counts, whatever its z
+ * (np.amin / np.amax over a whole column, pcl.py:307-308; point_cloud_2_ply.py:87). */
 int sd_slab_minmax(const float* d_x, const float* d_z, int n, double lo, double hi, int use_f32,
                    float* h_xmin, float* h_xmax, int32_t* h_count, SdWorkspace* ws, void* stream);
 

@@ -329,7 +329,8 @@ slab_kernel(const SlabJob* __restrict__ jobs) {
     uint32_t kmin = 0xffffffffu, kmax = 0u; int cnt = 0;
     for (int i = blockIdx.x * kSlabThreads + threadIdx.x; i < n; i += gridDim.x * kSlabThreads) {
         const float z = __ldg(J.z + i);
-        bool in = J.use_f32 ? ((z < J.hi32) && (z > J.lo32)) : (((double)z < J.hi) && ((double)z > J.lo));
+        // use_f32 == 2: no slab test at all (min / max over every row, +-inf and NaN depths included)
+        bool in = (J.use_f32 == 2) ? true : (J.use_f32 ? ((z < J.hi32) && (z > J.lo32)) : (((double)z < J.hi) && ((double)z > J.lo)));
         if (in) {
             uint32_t k = f2key(__ldg(J.x + i));
             kmin = min(kmin, k); kmax = max(kmax, k); ++cnt;

@@ -21,6 +21,17 @@ from ._lib import SdCamera, SdFrameResult, SdParams, SdPredicate, check
 from .params import FusionParams, Intrinsics
 
 
+def _on_device(fn):
+    """Run a per-call op with the engine's device current, so that the stream handed to the C ABI belongs to it."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 def _ptr(t):
     return C.c_void_p(0 if t is None else t.data_ptr())
 
@@ -322,11 +333,13 @@ class FusionEngine:
     # ------------------------------------------------------------------------------------------
     # per-call cloud ops (SoA device tensors in, device tensors / host scalars out)
     # ------------------------------------------------------------------------------------------
+    @_on_device
     def median_mad(self, col: torch.Tensor) -> tuple[np.float32, np.float32]:
         out = (C.c_float * 2)()
         check(self.lib.sd_median_mad(_ptr(col), col.numel(), out, self._ws, _stream_ptr()), "sd_median_mad")
         return np.float32(out[0]), np.float32(out[1])
 
+    @_on_device
     def filter(self, x, y, z, pred: SdPredicate, want_points: bool = True):
         """Stable filter; returns (kept_idx int32 [M], (x,y,z) of the survivors or None)."""
         n = x.numel()
@@ -342,6 +355,7 @@ class FusionEngine:
         pts = (ox[:m], oy[:m], oz[:m]) if want_points else None
         return idx[:m], pts
 
+    @_on_device
     def plane_fit(self, x, y, z, axis: int):
         coeff = (C.c_double * 3)()
         sing = C.c_int32(0)
@@ -349,17 +363,20 @@ class FusionEngine:
                                     _stream_ptr()), "sd_plane_fit")
         return np.array(list(coeff), dtype=np.float64), bool(sing.value)
 
+    @_on_device
     def mean_f32(self, col: torch.Tensor) -> np.float32:
         out = C.c_float(0)
         check(self.lib.sd_mean_f32(_ptr(col), col.numel(), C.byref(out), self._ws, _stream_ptr()), "sd_mean_f32")
         return np.float32(out.value)
 
+    @_on_device
     def slab_minmax(self, x, z, lo: float, hi: float, use_f32: bool):
         xmin, xmax, cnt = C.c_float(0), C.c_float(0), C.c_int32(0)
         check(self.lib.sd_slab_minmax(_ptr(x), _ptr(z), x.numel(), lo, hi, int(use_f32), C.byref(xmin), C.byref(xmax),
                                       C.byref(cnt), self._ws, _stream_ptr()), "sd_slab_minmax")
         return np.float32(xmin.value), np.float32(xmax.value), int(cnt.value)
 
+    @_on_device
     def knn_mean_distance(self, x, y, z, k: int, std_ratio: float = 0.5):
         n = x.numel()
         avg = torch.empty(max(n, 1), dtype=torch.float64, device=x.device)
@@ -368,6 +385,7 @@ class FusionEngine:
                                             _stream_ptr()), "sd_knn_mean_distance")
         return avg[:n], (stats[0], stats[1], stats[2])
 
+    @_on_device
     def radius_count(self, x, y, z, radius: float, cap: int = -1):
         n = x.numel()
         cnt = torch.empty(max(n, 1), dtype=torch.int32, device=x.device)
@@ -375,6 +393,7 @@ class FusionEngine:
               "sd_radius_count")
         return cnt[:n]
 
+    @_on_device
     def ransac_score(self, x, y, z, axis: int, threshold: float, triplets: torch.Tensor):
         k = triplets.shape[0]
         counts = torch.empty(k, dtype=torch.int32, device=x.device)

@@ -175,3 +175,75 @@ def registered_empty(nbytes: int) -> torch.Tensor:
         raise RuntimeError(f"cudaHostRegister failed: {rc}")
     buf._sd_owner = (_HostBlock(ptr, nbytes, lambda: rt.cudaHostUnregister(ctypes.c_void_p(ptr))), m)
     return t
+
+
+# ---------------------------------------------------------------------------------------------------
+# which GPUs of the box to use when the job has fewer ranks than the box has GPUs
+# ---------------------------------------------------------------------------------------------------
+def candidate_device_maps(world: int, visible: int) -> dict:
+    """Rank -> device maps worth trying when ``world < visible``: the first GPUs, the last GPUs, every
+    (visible/world)-th GPU.  On a two-socket box whose host memory sits behind one socket the GPUs of the other
+    socket share one inter-socket link for their host reads (measured on this pool's 8 x B200 boxes: GPUs 0-3
+    together get 115 GB/s, GPUs 4-7 together 221 GB/s, tools/h2d_probe.py), and a hypervisor can hide that
+    topology from sysfs -- so the maps are *measured*, not derived."""
+    maps = {"first": list(range(world))}
+    if visible > world:
+        maps["last"] = list(range(visible - world, visible))
+        maps["spread"] = [i * visible // world for i in range(world)]
+    return maps
+
+
+def measure_h2d_gbs(device: int, mbytes: int = 96, reps: int = 6, barrier=None) -> float:
+    """Pinned host -> device copy rate of ``device`` (two copies in flight, CUDA events).  ``barrier`` (a callable) is
+    invoked right before the timed copies so that all ranks of a job copy at the same time."""
+    nbytes = mbytes << 20
+    with torch.cuda.device(device):
+        src = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        dst = [torch.empty(nbytes, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(2)]
+        streams = [torch.cuda.Stream(device=device) for _ in range(2)]
+        for i in range(2):
+            src[i].fill_(i + 1)
+            with torch.cuda.stream(streams[i]):
+                dst[i].copy_(src[i], non_blocking=True)
+        torch.cuda.synchronize(device)
+        if barrier is not None:
+            barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in streams:
+            s.wait_event(e0)
+        for i in range(reps):
+            with torch.cuda.stream(streams[i % 2]):
+                dst[i % 2].copy_(src[i % 2], non_blocking=True)
+        for s in streams:
+            torch.cuda.current_stream().wait_stream(s)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1)
+        del src, dst
+        torch.cuda.empty_cache()
+    return reps * nbytes / (ms * 1e-3) / 1e9
+
+
+def choose_device(local_rank: int, world: int, all_reduce_min=None, barrier=None, min_gain: float = 1.10) -> tuple[int, dict]:
+    """Device for this rank.  With as many ranks as GPUs (or one rank) it is ``local_rank``.  Otherwise every
+    candidate map is timed with all ranks copying at once and the map with the best *slowest* rank wins (the
+    plain first-N map unless another one is at least ``min_gain`` x better).  ``all_reduce_min(x) -> float`` and
+    ``barrier()`` are the job's CPU-side collectives (gloo); without them the first-N map is used."""
+    visible = torch.cuda.device_count()
+    report = {"visible_gpus": visible, "world": world, "map": "first", "devices": list(range(min(world, visible)))}
+    if world <= 1 or visible <= world or all_reduce_min is None or os.environ.get("SD_DEVICE_MAP", "") == "first":
+        return local_rank % max(visible, 1), report
+    maps = candidate_device_maps(world, visible)
+    forced = os.environ.get("SD_DEVICE_MAP", "")
+    rates = {}
+    for name, m in maps.items():
+        if forced and name != forced:
+            continue
+        mine = measure_h2d_gbs(m[local_rank], barrier=barrier)
+        rates[name] = float(all_reduce_min(mine))
+    best = max(rates, key=lambda k: rates[k])
+    if "first" in rates and rates[best] < min_gain * rates["first"]:
+        best = "first"
+    report.update({"map": best, "devices": maps[best], "slowest_rank_h2d_gb_per_s": {k: round(v, 2) for k, v in rates.items()}})
+    return maps[best][local_rank], report

@@ -235,14 +235,17 @@ def get_end_points_of_segment(segment):
     c = _Cloud(segment)
     if c.n == 0:
         return None, None
-    inf = float("inf")
-    xmin, xmax, _ = c.eng.slab_minmax(c.x, c.z, -inf, inf, False)
+    xmin, xmax, _ = c.eng.slab_minmax(c.x, c.z, 0.0, 0.0, 2)          # every row, whatever its z (np.amin / np.amax)
+    if bool(torch.isnan(c.x).any()):                                  # np.amin / np.amax propagate NaN, and x == NaN selects no row
+        xmin = xmax = np.float32(np.nan)
     return _rows_equal(c, xmin), _rows_equal(c, xmax)
 
 
 def _rows_equal(c: _Cloud, value) -> object:
     # rows whose x equals the extreme: |x| < value+ and > value- cannot be expressed with one predicate;
     # x == v  <=>  not (x < v) and not (x > v); both extremes are attained, so use two cheap filters.
+    if value != value:                                                # NaN extreme: `x == nan` selects nothing
+        return c.take(c.src, torch.empty(0, dtype=torch.int32, device=c.device))
     lt = _keep(c, _pred(_lib.PRED_LT, 0, fa=float(value)))
     gt = _keep(c, _pred(_lib.PRED_GT, 0, fa=float(value)))
     mask = torch.ones(c.n, dtype=torch.bool, device=c.device)

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from ._lib import SdFrameResult
-from .engine import FusionEngine, FusionResult, RESULT_DTYPE
+from .engine import FusionEngine, FusionResult, RESULT_DTYPE, camera_struct
 from .params import FusionParams, Intrinsics
 
 
@@ -64,6 +64,13 @@ def gather_results(local: torch.Tensor, n_frames: int, device=None):
 # ---------------------------------------------------------------------------------------------
 # pipelined batches on one GPU
 # ---------------------------------------------------------------------------------------------
+def _cam_key(intr: Intrinsics) -> bytes:
+    """The camera is captured BY VALUE in a slot's CUDA graph (kernel arguments), so it is part of the graph's key: a
+    batch with other intrinsics -- the reference derives disparity_mult from each frame's width,
+    semantic_depth.py:109,145 -- gets its own capture instead of silently replaying the first camera."""
+    return bytes(camera_struct(intr))
+
+
 class _Slot:
     def __init__(self, height, width, batch, device, max_hyp=0):
         self.engine = FusionEngine(height, width, max_frames=batch, max_hypotheses=max_hyp, device=device)
@@ -167,7 +174,7 @@ class FramePipeline:
         slot, finished = self._take_slot()
         with torch.cuda.stream(slot.stream):
             slot.tag = tag
-            self._launch(slot, logits, disp, intr, key=(logits.data_ptr(), disp.data_ptr(), logits.shape[0]))
+            self._launch(slot, logits, disp, intr, key=(logits.data_ptr(), disp.data_ptr(), logits.shape[0], _cam_key(intr)))
         return finished
 
     def warm_device(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, tag=None):
@@ -192,7 +199,7 @@ class FramePipeline:
             slot.stage_logits[:b].copy_(lg, non_blocking=True)
             slot.stage_disp[:b].copy_(dp, non_blocking=True)
             slot.tag = tag
-            self._launch(slot, slot.stage_logits[:b], slot.stage_disp[:b], intr, key=("host", b))
+            self._launch(slot, slot.stage_logits[:b], slot.stage_disp[:b], intr, key=("host", b, _cam_key(intr)))
         return finished
 
     def submit_host_scores(self, scores, weights_dev: torch.Tensor, bias_dev: torch.Tensor, disp, intr: Intrinsics, tag=None):
@@ -211,7 +218,7 @@ class FramePipeline:
             slot.stage_scores[:b].copy_(sc, non_blocking=True)
             slot.stage_disp[:b].copy_(dp, non_blocking=True)
             slot.tag = tag
-            key = ("host_scores", b, weights_dev.data_ptr())
+            key = ("host_scores", b, weights_dev.data_ptr(), bias_dev.data_ptr(), _cam_key(intr))
             args = (slot.stage_scores[:b], weights_dev, bias_dev, slot.stage_disp[:b], intr, self.params)
             g = slot.graphs.get(key)
             if g is None and self.use_graphs:

@@ -69,15 +69,16 @@ class PointCloud2Ply():
         if n == 0:
             return b""
         x, y, z, rgb = self._device_cloud(points3D, colors)
-        eng = engine_for(n)
+        eng = engine_for(n, x.device)
         lib = _lib.load()
         capacity = 48 * n + 1024
         for _ in range(2):
             out = torch.empty(capacity, dtype=torch.uint8, device=x.device)
             nbytes = C.c_ulonglong(0)
             fn = lib.sd_ply_rows if x.dtype == torch.float32 else lib.sd_ply_rows_f64
-            rc = fn(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), n, out.data_ptr(), capacity,
-                                 C.byref(nbytes), eng._ws, torch.cuda.current_stream().cuda_stream)
+            with torch.cuda.device(x.device):
+                rc = fn(x.data_ptr(), y.data_ptr(), z.data_ptr(), rgb.data_ptr(), n, out.data_ptr(), capacity,
+                        C.byref(nbytes), eng._ws, torch.cuda.current_stream().cuda_stream)
             if rc == 0:
                 return out[: nbytes.value].cpu().numpy().tobytes()
             if nbytes.value <= capacity:
@@ -108,8 +109,8 @@ class PointCloud2Ply():
             # float32 columns, so this one predicate is evaluated with torch (same semantics: NaN minimum keeps nothing)
             idx = torch.nonzero(z > z.min()).reshape(-1).cpu().numpy().astype(np.int64)
         else:
-            eng = engine_for(n)
-            zmin, _, _ = eng.slab_minmax(z, z, -np.inf, np.inf, use_f32=True)      # min of z over all rows
+            eng = engine_for(n, z.device)
+            zmin, _, _ = eng.slab_minmax(z, z, 0.0, 0.0, use_f32=2)                # min of z over ALL rows (-inf included)
             if np.isnan(self.points3D[:, 2]).any():
                 zmin = np.float32(np.nan)                                           # np.min propagates NaN -> nothing is kept
             keep, _ = eng.filter(x, y, z, SdPredicate(kind=PRED_GT, axis=2, fa=float(zmin)), want_points=False)

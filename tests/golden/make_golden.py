@@ -295,7 +295,9 @@ def check_pixel_vectors(post_processing, compute_3D_points):
 def main():
     ref_pcl, post_processing, compute_3D_points = load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "--only-full-size":
-        check_frames(ref_pcl, post_processing, compute_3D_points, cases=FRAME_CASES[-1:])
+        # optional seeds after the flag: the frames of bench.py's first batch are seeds 0..4
+        seeds = [int(v) for v in sys.argv[2:]] or [0]
+        check_frames(ref_pcl, post_processing, compute_3D_points, cases=tuple((1024, 2048, sd) for sd in seeds))
         return
     # --verify: recompute everything from the live reference and compare with the committed files instead of writing
     verify = len(sys.argv) > 1 and sys.argv[1] == "--verify"

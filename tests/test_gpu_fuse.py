@@ -115,6 +115,41 @@ def test_fused_batch_graph_and_host_path(cuda_device):
     assert res4.raw.tobytes() == res.raw.tobytes()
 
 
+def test_pipeline_slot_sees_every_camera(cuda_device):
+    """A slot's CUDA graph captures the camera by value: batches with different intrinsics through the SAME slot must
+    each get their own camera (the reference derives disparity_mult per frame, semantic_depth.py:109,145)."""
+    from semantic_depth_b200.params import Intrinsics
+    from semantic_depth_b200.stream import FramePipeline
+    h, w, B = 128, 256, 2
+    logits, disp, intr_a = scene.make_batch(B, h, w, first_seed=31)
+    intr_b = Intrinsics(cx=intr_a.cx * 1.02, cy=intr_a.cy * 0.97, f=intr_a.f * 1.1, b=intr_a.b, disparity_mult=intr_a.disparity_mult * 1.25)
+    P = FusionParams()
+    want = {}
+    for tag, intr in (("a", intr_a), ("b", intr_b)):
+        want[tag] = [frame_ref.fuse_frame(logits[f], disp[f], intr.as_q32(), intr.disparity_mult, P) for f in range(B)]
+    assert want["a"][0]["counts"] != want["b"][0]["counts"]
+    pipe = FramePipeline(h, w, B, slots=1, device=cuda_device, params=P, use_graphs=True)
+    dl, dd = torch.from_numpy(logits).cuda(), torch.from_numpy(disp).cuda()
+    got = []
+    for tag, intr in (("a", intr_a), ("b", intr_b), ("a", intr_a), ("b", intr_b)):
+        fin = pipe.submit_device(dl, dd, intr, tag=tag)
+        if fin:
+            got.append(fin)
+    got += pipe.drain()
+    for tag, intr in (("a", intr_a), ("b", intr_b), ("b", intr_b)):
+        fin = pipe.submit_host(logits, disp, intr, tag=tag)
+        if fin:
+            got.append(fin)
+    got += pipe.drain()
+    assert [t for t, _ in got] == ["a", "b", "a", "b", "a", "b", "b"]
+    for tag, res in got:
+        for f in range(B):
+            o = want[tag][f]
+            assert res.counts(f) == {k: int(v) for k, v in o["counts"].items()}, (tag, f)
+            assert (o["rw"] is None and np.isnan(res.rw[f])) or float(res.rw[f]) == o["rw"], (tag, f)
+    pipe.close()
+
+
 @pytest.mark.parametrize("variant", ["rw_only", "no_sor", "no_ror", "no_filters", "depth20", "k16"])
 def test_fused_param_variants(cuda_device, variant):
     h, w = 256, 512

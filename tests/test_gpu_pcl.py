@@ -128,6 +128,22 @@ def test_end_points_of_road(cuda_device, vec, name):
             assert same(a[0], b[0]) and same(a[1], b[1]), (name, depth)
 
 
+def test_end_points_of_segment_with_non_finite_rows(cuda_device):
+    """pcl.py:307-308 take np.amin / np.amax over every row of the segment: rows whose z is +-inf or NaN count too."""
+    rng = np.random.default_rng(3)
+    seg = (rng.standard_normal((3000, 3)) * [3.0, 0.1, 10.0]).astype(np.float32)
+    seg[np.argmin(seg[:, 0]), 2] = -np.inf            # the leftmost row has z = -inf
+    seg[np.argmax(seg[:, 0]), 2] = np.nan             # the rightmost row has z = NaN
+    seg[7, 2] = np.inf
+    a, b = pcl_ref.get_end_points_of_segment(seg), pcl.get_end_points_of_segment(seg)
+    assert same(a[0], b[0]) and same(a[1], b[1])
+    seg[11, 0] = np.nan                               # NaN in x: amin / amax are NaN and `x == nan` selects no row
+    with np.errstate(invalid="ignore"):
+        a = pcl_ref.get_end_points_of_segment(seg)
+    b = pcl.get_end_points_of_segment(seg)
+    assert a[0].shape == b[0].shape == (0, 3) and a[1].shape == b[1].shape == (0, 3)
+
+
 def test_intersection_distance_line(cuda_device, vec):
     road = {"Cx": 0.01, "Cy": -1.0, "Cz": 0.002, "C": -1.5}
     left = {"Cx": -1.0, "Cy": 0.03, "Cz": 0.001, "C": -4.0}

@@ -79,3 +79,24 @@ def test_ply_cloud_plus_float64_line(cuda_device, tmp_path):
     w.prepare_and_save_point_cloud()
     want = ply_ref.prepare_and_save_bytes(np.vstack([road, line]), np.vstack([colors, line_colors]))
     assert open(tmp_path / "rw.ply", "rb").read() == want
+
+
+def test_ply_infinity_filter_with_minus_inf_rows(cuda_device, tmp_path):
+    """Disparity-0 pixels reproject to z = -inf: ``z > z.min()`` (point_cloud_2_ply.py:87-89) must drop exactly those rows
+    and keep every finite one, including the row at the finite minimum (the filter's minimum is taken over ALL rows)."""
+    rng = np.random.default_rng(5)
+    p = (rng.standard_normal((4000, 3)) * [3.0, 0.2, 15.0] + [0.0, -1.5, -30.0]).astype(np.float32)
+    p[::37, 2] = -np.inf
+    p[5, 2] = np.float32(p[np.isfinite(p[:, 2]), 2].min())          # two rows share the finite minimum
+    c = rng.integers(0, 256, p.shape).astype(np.uint8)
+    w = PointCloud2Ply(p.copy(), c.copy(), str(tmp_path / "inf"))
+    w.prepare_and_save_point_cloud()
+    got = open(tmp_path / "inf.ply", "rb").read()
+    assert got == ply_ref.prepare_and_save_bytes(p, c)
+    assert w.points3D.shape[0] == int(np.isfinite(p[:, 2]).sum())
+    # no -inf row: the reference drops the rows at the (finite) minimum -- same here
+    q = p[np.isfinite(p[:, 2])]
+    w2 = PointCloud2Ply(q.copy(), c[: len(q)].copy(), str(tmp_path / "fin"))
+    w2.prepare_and_save_point_cloud()
+    assert open(tmp_path / "fin.ply", "rb").read() == ply_ref.prepare_and_save_bytes(q, c[: len(q)])
+    assert w2.points3D.shape[0] == int((q[:, 2] > q[:, 2].min()).sum())

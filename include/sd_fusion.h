@@ -313,6 +313,25 @@ int sd_ws_enable_timing(SdWorkspace* ws, int enable);
 int sd_ws_set_stage_mask(SdWorkspace* ws, int mask);
 int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms);
 
+/* Per-stage device times of the last fused call, the counterpart of the reference's tic / toc pairs around every stage
+ * of process_frame (semantic_depth.py:157-190 segmentation / disparity / 3-D, :203-221 road denoising, :227-245 the two
+ * Open3D filters, :253-268 rw, :274-311 fences, :316-332 f2f; dumped at :445-454).  Needs sd_ws_enable_timing(ws, 1)
+ * and a full call (stage mask 15) outside stream capture; such a call keeps the fence chain on `stream` so that the
+ * stages are disjoint and add up.  h_ms [SD_NUM_STAGES], milliseconds, after the stream has been synchronised. */
+enum SdStage {
+    SD_STAGE_PIXEL = 0,        /* labels, disparity blend, x mult, reprojection, mask gather, remove_from_to */
+    SD_STAGE_ROAD_MAD = 1,     /* remove_noise_by_mad on y and on x */
+    SD_STAGE_ROAD_PLANE = 2,   /* remove_noise_by_fitting_plane (and the RANSAC scoring when hypotheses are given) */
+    SD_STAGE_ROAD_GRID = 3,    /* search grid of the two Open3D filters */
+    SD_STAGE_ROAD_KNN = 4,     /* statistical_outlier_removal: k-NN mean distances + cloud statistics */
+    SD_STAGE_ROAD_ROR = 5,     /* radius_outlier_removal + the compaction that applies both filters */
+    SD_STAGE_RW = 6,           /* get_end_points_of_road slab scan */
+    SD_STAGE_FENCES = 7,       /* the whole fence chain */
+    SD_STAGE_ANSWERS = 8,      /* rw, plane intersections, f2f */
+    SD_NUM_STAGES = 9
+};
+int sd_ws_stage_times(SdWorkspace* ws, float* h_ms);
+
 /* Device pointers of a frame's final clouds inside the workspace (valid until the next fuse call):
  * which = 0 road (after ROR), 1 left fence (after plane filter), 2 right fence. */
 int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,

@@ -37,6 +37,24 @@ def _run(kd_workers):
     return dt, o["rw"], o["f2f"]
 
 
+def _prepare_scores(seed):
+    from semantic_depth_b200 import scene
+    h, w = _FRAME["shape"]
+    _FRAME["scores"] = scene.make_frame_scores(h, w, seed)     # (second_skip scores, up-sampling weights, bias, disp, intr)
+    return seed
+
+
+def _run_scores(kd_workers):
+    """Score-map arm: the CPU also evaluates FCN-8s' last transposed convolution (fcn8s/fcn.py:207-213) before the path."""
+    from oracle import frame_ref
+    sc, wts, bs, disp, intr = _FRAME["scores"]
+    t = time.perf_counter()
+    logits = frame_ref.upsample_scores(sc, wts, bs)
+    o = frame_ref.fuse_frame(logits, disp, intr.as_q32(), intr.disparity_mult, workers=kd_workers)
+    dt = time.perf_counter() - t
+    return dt, o["rw"], o["f2f"]
+
+
 class CpuBaseline:
     """Pool of worker processes; ``step()`` runs one frame per worker and returns the wall time."""
 
@@ -65,6 +83,17 @@ class CpuBaseline:
         out = [r.get() for r in res]
         wall = time.perf_counter() - t
         return wall, self.procs, out
+
+    def step_scores(self):
+        """``step`` in the score-map mode (inputs = FCN-8s second_skip scores + disparities)."""
+        res = [p.apply_async(_prepare_scores, (self.seed + i,)) for i, p in enumerate(self.pools)]
+        for r in res:
+            r.get()
+        self.seed += self.procs
+        t = time.perf_counter()
+        res = [p.apply_async(_run_scores, (self.kd_workers,)) for p in self.pools]
+        out = [r.get() for r in res]
+        return time.perf_counter() - t, self.procs, out
 
     def close(self):
         for p in self.pools:

@@ -20,6 +20,8 @@ COUNT_NAMES = (
 )
 assert len(COUNT_NAMES) == SD_NUM_COUNTS
 
+STAGE_NAMES = ("pixel", "road_mad", "road_plane", "road_grid", "road_knn", "road_ror", "rw", "fences", "answers")
+
 (PRED_LT, PRED_ABS_LT, PRED_MAD, PRED_PLANE, PRED_GT, PRED_SLAB, PRED_SOR, PRED_ROR) = range(8)
 
 
@@ -99,6 +101,7 @@ SIGNATURES = {
     "sd_ws_enable_timing": (_I, [_P, _I]),
     "sd_ws_set_stage_mask": (_I, [_P, _I]),
     "sd_ws_stage_elapsed_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
+    "sd_ws_stage_times": (_I, [_P, C.POINTER(C.c_float)]),
     "sd_ws_cloud": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sd_ws_stage_src": (_I, [_P, _I, _I, C.POINTER(_P)]),
 }

@@ -97,6 +97,7 @@ struct WsPriv {
     SdCamera cam;
     double cell_scale;
     cudaEvent_t ev_t[3]; bool timing; int stage_mask;
+    cudaEvent_t ev_s[SD_NUM_STAGES + 1]; bool stages_valid;     // stage boundaries of the last timed call (profiling mode)
 };
 
 size_t carve_all(SdWorkspace* ws, Carver& c) {
@@ -295,7 +296,8 @@ extern "C" int sd_ws_create(SdWorkspace** out, void* d_mem, size_t bytes, int ma
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_fork, cudaEventDisableTiming));
     SD_CUDA_TRY(cudaEventCreateWithFlags(&pv->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 3; ++i) SD_CUDA_TRY(cudaEventCreate(&pv->ev_t[i]));
-    pv->timing = false; pv->stage_mask = 15;
+    for (int i = 0; i <= SD_NUM_STAGES; ++i) SD_CUDA_TRY(cudaEventCreate(&pv->ev_s[i]));
+    pv->timing = false; pv->stage_mask = 15; pv->stages_valid = false;
     const char* e = getenv("SD_FUSE_SINGLE_STREAM");
     pv->single_stream = (e && e[0] == '1');
     const char* cs = getenv("SD_KNN_CELL_SCALE");
@@ -314,6 +316,7 @@ extern "C" void sd_ws_destroy(SdWorkspace* ws) {
         if (pv->ev_fork) cudaEventDestroy(pv->ev_fork);
         if (pv->ev_join) cudaEventDestroy(pv->ev_join);
         for (int i = 0; i < 3; ++i) if (pv->ev_t[i]) cudaEventDestroy(pv->ev_t[i]);
+        for (int i = 0; i <= SD_NUM_STAGES; ++i) if (pv->ev_s[i]) cudaEventDestroy(pv->ev_s[i]);
         cudaFreeHost(ws->h_pinned);
     }
     delete ws;
@@ -538,7 +541,7 @@ extern "C" int sd_mean_f32(const float* d_col, int n, float* h_mean, SdWorkspace
     SD_CUDA_TRY(cudaMemcpyAsync(&cs->n_in, &n, sizeof(int), cudaMemcpyHostToDevice, st));
     MeanJob j{d_col, &cs->n_in, &cs->f[2], ws->mean_leaf};
     SD_CUDA_TRY(cudaMemcpyAsync(dj, &j, sizeof(j), cudaMemcpyHostToDevice, st));
-    rc = sd_launch_mean(dj, 1, st); if (rc) return rc;
+    rc = sd_launch_mean(dj, 1, ws->cap, st); if (rc) return rc;
     return download_sync(h_mean, &cs->f[2], 1, ws, st);
 }
 
@@ -801,6 +804,11 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
     const bool do_pixel = (sm_ & 1) != 0, do_pre = (sm_ & 2) != 0, do_knn = (sm_ & 4) != 0, do_post = (sm_ & 8) != 0;
     // ---- pixel stage: rA <- road (z cut applied), fA <- fence
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[0], st));
+    // profiling mode (sd_ws_enable_timing on a full, uncaptured call): every stage is bracketed and the fence chain stays on
+    // `st`, so the stage times add up to the call -- the reference's tic/toc pairs (semantic_depth.py:157-332)
+    const bool stages = timing && sm_ == 15;
+#define SD_MARK(k) do { if (stages) SD_CUDA_TRY(cudaEventRecord(pv->ev_s[k], st)); } while (0)
+    SD_MARK(0);
     rc = !do_pixel ? SD_OK : sd_launch_pixel(d_logits, d_disp, ws->lmask, ws->rmask, B, height, width, *cam, P.prob_thr, P.road_z_to_meter, 0,
                          ws->road[0], ws->fence[0], cap,
                          &ws->fs[0].n[SD_CNT_ROAD_GATHER], &ws->fs[0].n[SD_CNT_ROAD_Z], &ws->fs[0].n[SD_CNT_FENCE_GATHER], cnt_stride,
@@ -808,9 +816,10 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
                          d_scores, d_upw, d_upb, nullptr, P.label_mode);
     if (rc) return rc;
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[1], st));
+    SD_MARK(SD_STAGE_PIXEL + 1);
     if (!do_pre && !do_knn && !do_post) return SD_OK;
     cudaStream_t sf = st;    // fence chain stream
-    const bool fork = do_pre && P.approach_both && !pv->single_stream;
+    const bool fork = do_pre && P.approach_both && !pv->single_stream && !stages;
     if (fork) {
         sf = pv->side_stream;
         SD_CUDA_TRY(cudaEventRecord(pv->ev_fork, st));
@@ -825,16 +834,22 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
     SD_RUN(sd_launch_select_median(T.sel_road_x_med, B, cap, st));
     SD_RUN(sd_launch_select_median(T.sel_road_x_mad, B, cap, st));
     SD_RUN(sd_launch_compact(T.c_road_x, B, cap, st));
+    SD_MARK(SD_STAGE_ROAD_MAD + 1);
     if (d_hyp_road) SD_RUN(sd_launch_ransac(T.r_road, B, cap, n_hyp, st));
     SD_RUN(sd_launch_plane(T.p_road, B, cap, st));
     SD_RUN(sd_launch_compact(T.c_road_plane, B, cap, st));
+    SD_MARK(SD_STAGE_ROAD_PLANE + 1);
     if (P.use_sor || P.use_ror) SD_RUN(sd_launch_grid_build(T.k_road, B, cap, st));
+    SD_MARK(SD_STAGE_ROAD_GRID + 1);
     }
     if (do_knn && P.use_sor) SD_RUN(sd_launch_knn(T.k_road, B, cap, P.sor_nb_neighbors, st));
+    SD_MARK(SD_STAGE_ROAD_KNN + 1);
     if (do_post && P.use_ror) SD_RUN(sd_launch_radius(T.k_road, B, cap, st));
     if (do_post) {
         SD_RUN(sd_launch_compact(T.c_road_final, B, cap, st));
+        SD_MARK(SD_STAGE_ROAD_ROR + 1);
         SD_RUN(sd_launch_slab(T.s_road, B, cap, st));
+        SD_MARK(SD_STAGE_RW + 1);
     }
     // ---- fence chain (stream sf)
     if (do_pre && P.approach_both) {
@@ -842,7 +857,7 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
         SD_RUN(sd_launch_select_median(T.sel_fence_y_mad, B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_fence_y, B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_fence_z, B, cap, sf));
-        SD_RUN(sd_launch_mean(T.m_fence, B, sf));
+        SD_RUN(sd_launch_mean(T.m_fence, B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_split, 2 * B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_side_x_med, 2 * B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_side_x_mad, 2 * B, cap, sf));
@@ -855,8 +870,12 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
         SD_CUDA_TRY(cudaEventRecord(pv->ev_join, sf));
         SD_CUDA_TRY(cudaStreamWaitEvent(st, pv->ev_join, 0));
     }
+    SD_MARK(SD_STAGE_FENCES + 1);
     if (do_post) SD_RUN(sd_launch_finalize(T.fin, B, &P, st));
 #undef SD_RUN
+    SD_MARK(SD_STAGE_ANSWERS + 1);
+#undef SD_MARK
+    pv->stages_valid = stages;
     if (timing) SD_CUDA_TRY(cudaEventRecord(pv->ev_t[2], st));
     return SD_OK;
 }
@@ -926,6 +945,14 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
     if (!ws || !h_ms || which < 0 || which > 1) return fail(SD_ERR_INVALID, "sd_ws_stage_elapsed_ms: bad argument");
     WsPriv* pv = priv(ws);
     SD_CUDA_TRY(cudaEventElapsedTime(h_ms, pv->ev_t[0], pv->ev_t[which == 0 ? 1 : 2]));
+    return SD_OK;
+}
+
+extern "C" int sd_ws_stage_times(SdWorkspace* ws, float* h_ms) {
+    if (!ws || !h_ms) return fail(SD_ERR_INVALID, "sd_ws_stage_times: null argument");
+    WsPriv* pv = priv(ws);
+    if (!pv->stages_valid) return fail(SD_ERR_UNSUPPORTED, "sd_ws_stage_times: the last fused call was not a full, uncaptured call with timing enabled");
+    for (int k = 0; k < SD_NUM_STAGES; ++k) SD_CUDA_TRY(cudaEventElapsedTime(&h_ms[k], pv->ev_s[k], pv->ev_s[k + 1]));
     return SD_OK;
 }
 

@@ -237,25 +237,23 @@ __device__ float combine_levels(const float* vals, int n, int path, int levels, 
     return ret;
 }
 
-// One CTA of 1024 threads per job.
-//   A. leaf sums: 8 lanes per leaf play NumPy's 8 strided accumulators (coalesced loads), combined as
-//      ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) by three xor-shuffles, then the n%8 tail; a leaf (>= 64
-//      elements whenever n > 128) is owned by the 64-element slot its start falls in
-//   B. thread t sums the leaf sums of the depth-10 subtree reached by the bits of t, in tree order
+// Leaf sums across the whole GPU, then one CTA of 1024 threads per job for the tree above them.
+//   A. (mean_leaf_kernel, many CTAs per job) leaf sums: 8 lanes per leaf play NumPy's 8 strided accumulators
+//      (coalesced loads), combined as ((r0+r1)+(r2+r3)) + ((r4+r5)+(r6+r7)) by three xor-shuffles, then the n%8
+//      tail; a leaf (>= 64 elements whenever n > 128) is owned by the 64-element slot its start falls in
+//   B. (mean_kernel) thread t sums the leaf sums of the depth-10 subtree reached by the bits of t, in tree order
 //   C. 32 lanes combine levels 5..9, one lane levels 0..4; mean = fl32(sum / fl32(n))
 __global__ void __launch_bounds__(kMeanThreads)
-mean_kernel(const MeanJob* __restrict__ jobs) {
-    __shared__ float s_sub[kMeanThreads];
-    __shared__ float s_mid[32];
-    const MeanJob J = jobs[blockIdx.x];
+mean_leaf_kernel(const MeanJob* __restrict__ jobs) {
+    const MeanJob J = jobs[blockIdx.y];
     const int n = *J.n;
     const int t = threadIdx.x;
     const float* __restrict__ a = J.col;
-    // ---- A (the slot loop has the same trip count for every thread of the CTA)
+    // the slot loop has the same trip count for every thread of a CTA
     const int grp = t >> 3, j = t & 7, ngroups = kMeanThreads >> 3;
     const int nslots = (n + 63) >> 6;
-    if (n == 0 && t == 0) J.leaf[0] = 0.f;
-    for (int s0 = 0; s0 < nslots; s0 += ngroups) {
+    if (n == 0 && t == 0 && blockIdx.x == 0) J.leaf[0] = 0.f;
+    for (int s0 = blockIdx.x * ngroups; s0 < nslots; s0 += gridDim.x * ngroups) {
         const int slot = s0 + grp;
         int off = 0, len = 0;
         bool owner = false;
@@ -282,7 +280,15 @@ mean_kernel(const MeanJob* __restrict__ jobs) {
             J.leaf[slot] = res;
         }
     }
-    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kMeanThreads)
+mean_kernel(const MeanJob* __restrict__ jobs) {
+    __shared__ float s_sub[kMeanThreads];
+    __shared__ float s_mid[32];
+    const MeanJob J = jobs[blockIdx.x];
+    const int n = *J.n;
+    const int t = threadIdx.x;
     // ---- B: descend kMeanDepth levels following the bits of t (MSB first)
     int off = 0, len = n; bool owner = true; int d = 0;
     for (; d < kMeanDepth; ++d) {
@@ -355,9 +361,11 @@ int sd_launch_compact(const sd::CompactJob* d_jobs, int njobs, int cap, cudaStre
     return SD_OK;
 }
 
-int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, cudaStream_t st) {
+int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, int cap, cudaStream_t st) {
     using namespace sd;
     if (njobs <= 0) return SD_OK;
+    // leaf sums: 64-element slots, 128 per CTA and trip; enough CTAs for one trip of a full-size column, at most a wave
+    mean_leaf_kernel<<<dim3(max(1, min(ceil_div(cap, 64 * (kMeanThreads >> 3)), (148 * 2) / njobs)), njobs), kMeanThreads, 0, st>>>(d_jobs);
     mean_kernel<<<njobs, kMeanThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;

@@ -21,7 +21,10 @@ constexpr int kScanTile = 4096;                                 // cell-count sc
 constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job
 constexpr int kPlaneSums = 9;
 constexpr int kMaxKnnK = 64;
-constexpr int kLevels = 3;                                      // grid resolutions of the neighbour search (cell edge x4 per level)
+#ifndef SD_KNN_LEVELS
+#define SD_KNN_LEVELS 3
+#endif
+constexpr int kLevels = SD_KNN_LEVELS;                                      // grid resolutions of the neighbour search (cell edge x4 per level)
 
 // ---- device-side per-frame scalars --------------------------------------------------------------
 struct FrameState {
@@ -266,7 +269,7 @@ struct SdWorkspace {
 int sd_launch_select_median(const sd::SelJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_compact(const sd::CompactJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_plane(const sd::PlaneJob* d_jobs, int njobs, int cap, cudaStream_t st);
-int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, cudaStream_t st);
+int sd_launch_mean(const sd::MeanJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_slab(const sd::SlabJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_grid_build(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t st);
 int sd_launch_knn(const sd::KnnJob* d_jobs, int njobs, int cap, int k, cudaStream_t st);

@@ -20,6 +20,7 @@
 // Not HBM-bound: the sorted copies (<= 3 x 5.4 MB per frame) live in L2/L1; the cost is instruction
 // issue + L1/L2 latency.
 #include "sd_internal.cuh"
+#include <cstdlib>
 
 namespace sd {
 
@@ -357,7 +358,9 @@ template <int K> struct KnnCfg {
     static constexpr int feed_cap = 4 * K + 24;                           // ... ring mode
     static constexpr int list_raw = 3 * K + 10;
     static constexpr int list_cap = list_raw > 126 ? 126 : list_raw;      // phase-2 list entries per query (smem, 7-bit slots)
-    static constexpr size_t smem_bytes = ((size_t)(list_cap + 1) * sizeof(int) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;   // + 1 spare row
+    // list entries are 16 bits: (row run of the query << 12) | offset inside that run (runs hold at most kExtreme = 4096
+    // candidates); a small shared-memory footprint leaves the L1 to the sorted copies, which is what the sweeps wait on
+    static constexpr size_t smem_bytes = ((size_t)(list_cap + 1) * sizeof(uint16_t) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;   // + 1 spare row
 };
 
 template <int KS>
@@ -400,7 +403,9 @@ struct UNetK {
 
 __device__ __forceinline__ float key_of(const float4& p, float qx, float qy, float qz) {
     const float fx = p.x - qx, fy = p.y - qy, fz = p.z - qz;
-    return (fx * fx + fy * fy) + fz * fz;               // identical expression in every phase
+    // fused multiply-adds: fewer roundings than the error bound kKeyErr assumes, two instructions less per candidate;
+    // the SAME expression in every phase (bound, collect, select) and in the radius pre-test
+    return __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, fx * fx));
 }
 __device__ __forceinline__ float key_f32(const KnnJob& J, int j, float qx, float qy, float qz) {
     return key_of(__ldg(J.sp + j), qx, qy, qz);
@@ -487,7 +492,7 @@ constexpr int kExtreme = 4096;                  // ... and beyond this it goes t
 #define SD_KNN_WAVES 16     // CTAs launched per SM (4 are resident; CTAs claim work until the queue is empty)
 #endif
 #ifndef SD_KNN_MINB
-#define SD_KNN_MINB 4
+#define SD_KNN_MINB 5       // resident CTAs per SM (96 registers; measured on B200: 4 -> 1.108 ms, 5 -> 1.063 ms, 6 spills -> 1.12 ms per 5-frame batch)
 #endif
 template <int KS>
 __global__ void __launch_bounds__(kKnnThreads, (KS <= 11 ? SD_KNN_MINB : 1))
@@ -498,7 +503,8 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
     constexpr int kListCap = Cfg::list_cap;
     extern __shared__ int2 s_dyn[];
     int2 (*s_seg)[kKnnThreads] = reinterpret_cast<int2 (*)[kKnnThreads]>(s_dyn);                   // (start, end) of a row run
-    int (*s_list)[kKnnThreads] = reinterpret_cast<int (*)[kKnnThreads]>(s_dyn + kMaxRows * kKnnThreads);   // candidate indices
+    uint16_t (*s_list)[kKnnThreads] = reinterpret_cast<uint16_t (*)[kKnnThreads]>(s_dyn + kMaxRows * kKnnThreads);   // candidates: (run << 12) | offset
+    auto listed = [&](int e, int t) -> int { const unsigned v = s_list[e][t]; return s_seg[v >> 12][t].x + (int)(v & 4095u); };
     const KnnJob J = jobs[blockIdx.y];
     const GridRt g = load_grid(J.gs);
     const int keff = min(J.k, g.n);
@@ -631,11 +637,17 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                             for (int u = 0; u < kBatch; ++u) c[u] = __ldg(pc + u);
 #pragma unroll
                             for (int u = 0; u < kBatch; ++u) {
-                                if (key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = j0 + u; ++cnt; }
+                                if (key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = (uint16_t)((ri << 12) | (j0 + u - se.x)); ++cnt; }
                             }
                         }
-                        for (; j0 < se.y; ++j0) {
-                            if (key_f32(J, j0, qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = j0; ++cnt; }
+                        if (j0 < se.y) {                                     // the tail as one masked batch: one round trip, not up to kBatch - 1
+                            float4 c[kBatch];
+#pragma unroll
+                            for (int u = 0; u < kBatch - 1; ++u) c[u] = __ldg(J.sp + min(j0 + u, se.y - 1));
+#pragma unroll
+                            for (int u = 0; u < kBatch - 1; ++u) {
+                                if (j0 + u < se.y && key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = (uint16_t)((ri << 12) | (j0 + u - se.x)); ++cnt; }
+                            }
                         }
                     }
                 }
@@ -644,26 +656,19 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                     const int ld = __ffs(hm) - 1;
                     const float hx = __shfl_sync(SD_FULL, qx, ld), hy = __shfl_sync(SD_FULL, qy, ld), hz = __shfl_sync(SD_FULL, qz, ld);
                     const float hband = __shfl_sync(SD_FULL, band, ld);
-                    const double h0 = __shfl_sync(SD_FULL, q0, ld), h1 = __shfl_sync(SD_FULL, q1, ld), hrad = __shfl_sync(SD_FULL, rad, ld);
-                    const int hLs = __shfl_sync(SD_FULL, Ls, ld), hk1 = __shfl_sync(SD_FULL, k1, ld);
-                    const int hrlo = __shfl_sync(SD_FULL, rlo, ld), hrhi = __shfl_sync(SD_FULL, rhi, ld);
+                    const int hnr = __shfl_sync(SD_FULL, nruns, ld);
                     const int htid = (tid & ~31) + ld;
-                    const LevelRt hv = level_of(J, g, hLs);
                     int hcnt = 0;
-                    for (int row0 = hrlo; row0 <= hrhi; row0 += 32) {
-                        int ms = 0, me = 0;
-                        if (row0 + lane_id() <= hrhi) row_run(g, hv, h0, h1, hrad, hk1, row0 + lane_id(), ms, me);
-                        const int nr = min(32, hrhi - row0 + 1);
-                        for (int r = 0; r < nr; ++r) {
-                            const int s = __shfl_sync(SD_FULL, ms, r), e = __shfl_sync(SD_FULL, me, r);
-                            for (int j0 = s; j0 < e; j0 += 32) {
-                                const int j = j0 + lane_id();
-                                const bool in = (j < e) && key_of(__ldg(J.sp + min(j, e - 1)), hx, hy, hz) <= hband;
-                                const unsigned bm = __ballot_sync(SD_FULL, in);
-                                const int slot = hcnt + __popc(bm & ((1u << lane_id()) - 1u));
-                                if (in && slot < kListCap) s_list[slot][htid] = j;
-                                hcnt += __popc(bm);
-                            }
+                    __syncwarp();                                        // the lane's staged runs are read by the whole warp
+                    for (int ri = 0; ri < hnr; ++ri) {
+                        const int2 se = s_seg[ri][htid];
+                        for (int j0 = se.x; j0 < se.y; j0 += 32) {
+                            const int j = j0 + lane_id();
+                            const bool in = (j < se.y) && key_of(__ldg(J.sp + min(j, se.y - 1)), hx, hy, hz) <= hband;
+                            const unsigned bm = __ballot_sync(SD_FULL, in);
+                            const int slot = hcnt + __popc(bm & ((1u << lane_id()) - 1u));
+                            if (in && slot < kListCap) s_list[slot][htid] = (uint16_t)((ri << 12) | (j - se.x));
+                            hcnt += __popc(bm);
                         }
                     }
                     __syncwarp();
@@ -675,7 +680,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 if (!__any_sync(SD_FULL, todo)) break;
                 if (todo) {
                     net.init();
-                    for (int e = 0; e < kListCap; ++e) net.feed(key_f32(J, s_list[e][tid], qx, qy, qz));
+                    for (int e = 0; e < kListCap; ++e) net.feed(key_f32(J, listed(e, tid), qx, qy, qz));
                     band = fminf(band, net.get(keff - 1) * (1.0f + 4.0f * kKeyErr));
                 }
             }
@@ -702,7 +707,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
             for (int e0 = 0; e0 < cnt; e0 += kBatch) {
                 float4 c[kBatch];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u) c[u] = __ldg(J.sp + s_list[min(e0 + u, cnt - 1)][tid]);
+                for (int u = 0; u < kBatch; ++u) c[u] = __ldg(J.sp + listed(min(e0 + u, cnt - 1), tid));
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) {
                     const uint32_t kb = __float_as_uint(key_of(c[u], qx, qy, qz));
@@ -717,7 +722,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 float4 w[kBatch];
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u)
-                    if (p0 + u < K) w[u] = __ldg(J.sp + s_list[(p0 + u < keff) ? (un.d[p0 + u] & ((1u << kSlotBits) - 1u)) : 0][tid]);
+                    if (p0 + u < K) w[u] = __ldg(J.sp + listed((p0 + u < keff) ? (int)(un.d[p0 + u] & ((1u << kSlotBits) - 1u)) : 0, tid));
 #pragma unroll
                 for (int u = 0; u < kBatch; ++u) {
                     if (p0 + u < K) {
@@ -738,7 +743,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
 #pragma unroll
                 for (int p = 0; p < K; ++p) bd[p] = inf;
                 for (int e = 0; e < cnt; ++e) {
-                    double v = dist2_f64(J, s_list[e][tid], qx, qy, qz);
+                    double v = dist2_f64(J, listed(e, tid), qx, qy, qz);
 #pragma unroll
                     for (int p = 0; p < K; ++p) { const double lo = fmin(bd[p], v); v = fmax(bd[p], v); bd[p] = lo; }
                 }
@@ -1150,6 +1155,13 @@ static int launch_knn_t(const sd::KnnJob* d_jobs, dim3 grid, cudaStream_t st) {
     static bool configured = false;       // per instantiation; the attribute is per function
     if (!configured) {
         SD_CUDA_TRY(cudaFuncSetAttribute(knn_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // shared-memory carve-out: just what the resident CTAs need, the rest of the 256 KB stays L1 (the sweeps wait on
+        // scattered reads of the sorted copies); SD_KNN_CARVEOUT (percent) overrides for experiments
+        const char* cv = getenv("SD_KNN_CARVEOUT");
+        const int blocks = (KS <= 11 ? SD_KNN_MINB : 1);
+        int pct = cv ? atoi(cv) : (int)(((smem + 1024 + 3584) * blocks * 100 + 228 * 1024 - 1) / (228 * 1024)) + 1;
+        if (pct > 100) pct = 100;
+        if (pct >= 0) SD_CUDA_TRY(cudaFuncSetAttribute(knn_kernel<KS>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         configured = true;
     }
     knn_kernel<KS><<<grid, kKnnThreads, smem, st>>>(d_jobs);

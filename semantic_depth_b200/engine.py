@@ -230,6 +230,14 @@ class FusionEngine:
         check(self.lib.sd_ws_stage_elapsed_ms(self._ws, {"pixel": 0, "total": 1}[which], C.byref(ms)), "sd_ws_stage_elapsed_ms")
         return float(ms.value)
 
+    def stage_times(self) -> dict:
+        """Device time in ms of every stage of the last ``fuse_frames`` call (after ``enable_timing(True)``): the
+        reference's tic / toc pairs of process_frame (semantic_depth.py:157-332, dumped at :445-454).  In this
+        profiling mode the fence chain runs on the same stream as the road chain, so the stages add up."""
+        ms = (C.c_float * len(_lib.STAGE_NAMES))()
+        check(self.lib.sd_ws_stage_times(self._ws, ms), "sd_ws_stage_times")
+        return {n: float(v) for n, v in zip(_lib.STAGE_NAMES, ms)}
+
     def final_cloud(self, frame: int, which: str = "road"):
         """(points [N,3] fp32, src [N] int32) of a frame's final road / left / right cloud (device)."""
         idx = {"road": 0, "left": 1, "right": 2}[which]

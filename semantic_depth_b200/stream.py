@@ -84,6 +84,7 @@ class _Slot:
         self.busy = False
         self.tag = None
         self.nbytes = 0
+        self.timed_total = False   # ev[0] / ev[4] bracket the batch (set by _launch; the score-map path records no brackets)
 
 
 class FramePipeline:
@@ -115,6 +116,7 @@ class FramePipeline:
         if self.timing:
             self.pixel_ms.append(slot.ev[0].elapsed_time(slot.ev[1]))
             self.knn_ms.append(slot.ev[2].elapsed_time(slot.ev[3]))
+        if self.timing or slot.timed_total:
             self.total_ms.append(slot.ev[0].elapsed_time(slot.ev[4]))
         raw = np.frombuffer(slot.host_results[: slot.nbytes].numpy().tobytes(), dtype=RESULT_DTYPE).copy()
         slot.busy = False
@@ -149,7 +151,9 @@ class FramePipeline:
                     gk.replay()
                 slot.ev[4].record(slot.stream)
             else:
+                slot.ev[0].record(slot.stream)
                 g[0].replay()
+                slot.ev[4].record(slot.stream)
         elif self.timing:
             for k, m in enumerate((1, 2, 4, 8)):
                 slot.ev[k].record(slot.stream)
@@ -157,11 +161,14 @@ class FramePipeline:
             eng.set_stage_mask(15)
             slot.ev[4].record(slot.stream)
         else:
+            slot.ev[0].record(slot.stream)
             eng.enqueue(logits, disp, intr, self.params)
+            slot.ev[4].record(slot.stream)
         slot.nbytes = b * C.sizeof(SdFrameResult)
         slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
         slot.done.record(slot.stream)
         slot.busy = True
+        slot.timed_total = True
 
     def _take_slot(self):
         slot = self.slots[self._next]
@@ -239,6 +246,7 @@ class FramePipeline:
                     e.record(slot.stream)
             slot.done.record(slot.stream)
             slot.busy = True
+            slot.timed_total = False
         return finished
 
     def drain(self):

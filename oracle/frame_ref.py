@@ -90,10 +90,18 @@ def _cubic_tables(src_n, dst_n):
 def resize_cubic_u8(img, dst_w, dst_h):
     """``cv2.resize(frame, (w, h), interpolation=cv2.INTER_CUBIC)`` on uint8 (semantic_depth.py:110-112).
 
-    OpenCV's fixed-point definition: bicubic weights (A = -0.75) evaluated in fp32 and rounded to 11 fractional
-    bits, an integer horizontal pass, an integer vertical pass, ``(v + 2^21) >> 22`` and saturation.  cv2's SIMD
-    builds evaluate the vertical pass in fp32 for the vectorised part of each row, so cv2 itself differs from this
-    definition by at most 1 LSB on a machine-dependent subset of pixels (tests/golden/make_golden.py records it).
+    OpenCV's own implementation (imgproc/src/resize.cpp, 4.13, the code that runs with ``cv2.ipp.setUseIPP(False)``):
+    bicubic weights (A = -0.75) evaluated in fp32 and rounded to 11 fractional bits (``saturate_cast<short>``, no
+    sum fix-up), an integer horizontal pass into a row buffer of ``dst_w * channels`` ints, and a vertical pass that is
+
+    * fp32 for the first ``8 * floor(dst_w * channels / 8)`` elements of every row (``VResizeCubicVec_32s8u``, 8 x int16
+      lanes at the SSE baseline the wheel is built for): ``S0*b0 + (S1*b1 + (S2*b2 + S3*b3))`` with ``b = beta * 2^-22``,
+      every product and sum rounded to fp32 (no FMA), round-half-even, saturation;
+    * integer for the tail of the row: ``(sum + 2^21) >> 22``, saturation.
+
+    Pinned byte for byte against cv2 with IPP off (tests/golden/make_golden_resize.py).  With IPP on (the wheel's
+    default) cv2 dispatches to Intel's closed-source ippiResizeCubic, which differs from OpenCV's own code by 1 LSB in
+    up to 4 % of the bytes and depends on the CPU it runs on: that path has no definition to be equal to.
     """
     img = np.asarray(img, dtype=np.uint8)
     if img.ndim == 2:
@@ -105,11 +113,21 @@ def resize_cubic_u8(img, dst_w, dst_h):
     hor = np.zeros((h, dst_w, c), np.int64)
     for k in range(4):
         hor += S[:, xi[:, k], :] * xa[None, :, k, None]
-    out = np.zeros((dst_h, dst_w, c), np.int64)
+    n = dst_w * c
+    hor = hor.reshape(h, n)
+    out = np.zeros((dst_h, n), np.int64)
     for k in range(4):
-        out += hor[yi[:, k], :, :] * yb[:, k, None, None]
-    out = (out + (1 << 21)) >> 22
-    return np.clip(out, 0, 255).astype(np.uint8)
+        out += hor[yi[:, k], :] * yb[:, k, None]
+    out = np.clip((out + (1 << 21)) >> 22, 0, 255)
+    nv = (n // 8) * 8
+    if nv:
+        b = yb.astype(np.float32) * np.float32(2.0 ** -22)                 # exact
+        rows = [hor[yi[:, k], :nv].astype(np.float32) for k in range(4)]   # |values| < 2^24: exact
+        acc = rows[3] * b[:, 3, None]
+        for k in (2, 1, 0):
+            acc = (rows[k] * b[:, k, None]).astype(np.float32) + acc       # fp32 product, fp32 sum
+        out[:, :nv] = np.clip(np.rint(acc.astype(np.float32)), 0, 255).astype(np.int64)
+    return out.astype(np.uint8).reshape(dst_h, dst_w, c)
 
 
 def labels_argmax(logits):

@@ -6,7 +6,8 @@
 // first point* (keeps the normal equations well conditioned), per-CTA partials are merged in a fixed
 // order by the last CTA of the job (deterministic), which also solves the 3x3 system.  Coefficients
 // agree with gelsd to ~1e-13 relative, so inlier sets match unless a residual lies within ~1e-12 of
-// the threshold (documented tie class).
+// the threshold (documented tie class).  A rank-deficient cloud gets gelsd's minimum-norm
+// solution (closed form on the centred moments), so the chain continues exactly like the reference's.
 #include "sd_internal.cuh"
 
 namespace sd {
@@ -90,13 +91,40 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
             const double det = cuu * cvv - cuv * cuv;
             const double scale = cuu * cvv;
             if (!(det > 1e-14 * scale) || !(scale > 0.0)) {
-                c0 = c1 = c2 = qnan;                   // rank-deficient cloud (gelsd would return a
-                if (J.status) atomicOr(J.status, (uint32_t)SD_ST_SINGULAR_FIT);   // min-norm answer)
+                // Rank-deficient design matrix [u v 1]: scipy.linalg.lstsq (gelsd, pcl.py:120,154,186) returns the
+                // MINIMUM-NORM least-squares solution in the original coordinates and the chain continues.  The ones
+                // column is always independent, so the rank is 1 + rank of the centred 2x2 moment matrix:
+                //   rank 0 (all (u, v) equal): one equation c0*um + c1*vm + c2 = wm  ->  C = wm * (um, vm, 1) / (um^2 + vm^2 + 1)
+                //   rank 1 (collinear (u, v), e.g. a constant column): (c0, c1) = p + t * e_perp along the null direction,
+                //           c2 = wm - c0*um - c1*vm; t minimises |C|^2.
+                // (u, v) collinear only up to rounding sit on gelsd's own rank cut-off (rcond = eps): documented tie class.
+                const double um = (double)u0 + Su / N, vm = (double)v0 + Sv / N, wm = (double)w0 + Sw / N;
+                const double tr = cuu + cvv;
+                if (!(tr > 0.0)) {
+                    const double q = 1.0 / (um * um + vm * vm + 1.0);
+                    c0 = wm * um * q; c1 = wm * vm * q; c2 = wm * q;
+                } else {
+                    double e0, e1;                                         // unit eigenvector of the non-zero eigenvalue (= tr)
+                    if (cuu >= cvv) { e0 = cuu; e1 = cuv; } else { e0 = cuv; e1 = cvv; }
+                    const double en = sqrt(e0 * e0 + e1 * e1);
+                    e0 /= en; e1 /= en;
+                    const double pr = (e0 * cuw + e1 * cvw) / tr;          // particular solution p = e (e . r) / lambda
+                    const double p0 = e0 * pr, p1 = e1 * pr;
+                    const double a2 = wm - p0 * um - p1 * vm;              // C(t) = a + t d
+                    const double d0 = -e1, d1 = e0, d2 = e1 * um - e0 * vm;
+                    const double t = -(p0 * d0 + p1 * d1 + a2 * d2) / (d0 * d0 + d1 * d1 + d2 * d2);
+                    c0 = p0 + t * d0; c1 = p1 + t * d1; c2 = a2 + t * d2;
+                }
             } else {
                 c0 = (cuw * cvv - cvw * cuv) / det;
                 c1 = (cvw * cuu - cuw * cuv) / det;
                 const double c2s = (Sw - c0 * Su - c1 * Sv) / N;        // intercept in shifted coordinates
                 c2 = ((double)w0 + c2s) - c0 * (double)u0 - c1 * (double)v0;
+            }
+            // non-finite moments (inf / NaN coordinates): no plane; scipy's lstsq refuses such input
+            if (!(isfinite(c0) && isfinite(c1) && isfinite(c2))) {
+                c0 = c1 = c2 = qnan;
+                if (J.status) atomicOr(J.status, (uint32_t)SD_ST_SINGULAR_FIT);
             }
         }
         J.coeff[0] = c0; J.coeff[1] = c1; J.coeff[2] = c2;

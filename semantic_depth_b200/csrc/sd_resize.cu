@@ -1,8 +1,9 @@
 // cv2.resize(frame, (w, h), interpolation=cv2.INTER_CUBIC) on 8-bit frames: the first thing process_frame does
 // with every frame (semantic_depth.py:110-112; SURVEY.md 8f rank 1 -- 54.7 % of the thesis' end-to-end time).
 //
-// OpenCV's fixed-point definition: bicubic weights (A = -0.75) evaluated in fp32 and rounded to 11 fractional bits
-// (saturate_cast<short>(c * 2048)), an integer horizontal pass, an integer vertical pass, (v + 2^21) >> 22, saturation.
+// OpenCV's own implementation (imgproc/src/resize.cpp 4.13, what runs with IPP off): bicubic weights (A = -0.75) evaluated in
+// fp32 and rounded to 11 fractional bits (saturate_cast<short>(c * 2048)), an integer horizontal pass, and a vertical pass that
+// is fp32 on the SIMD part of each row and integer ((v + 2^21) >> 22) on its tail; saturation.  Byte-identical to cv2.
 // One thread per output pixel computes its own 4 + 4 weights (the fp32 expressions of interpolateCubic, evaluated in
 // the same order; -fmad=false) and the 4 x 4 x channels integer taps.  The frame is read once (each source pixel
 // belongs to about one window when shrinking by 4), so the kernel is HBM-bound: src bytes in + dst bytes out.
@@ -42,29 +43,42 @@ resize_cubic_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ ds
     if (dx >= dst_w || dy >= dst_h) return;
     const uint8_t* s = src + (size_t)blockIdx.z * src_h * src_w * C;
     const CubicTap tx = cubic_tap(dx, src_w, scale_x), ty = cubic_tap(dy, src_h, scale_y);
-    long long acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0;
+    // horizontal pass: the four row-buffer values of this output pixel (ints), per channel
+    int hrow[4][C];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const uint8_t* row = s + (size_t)ty.idx[r] * src_w * C;
-        int h[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) h[c] = 0;
+        for (int c = 0; c < C; ++c) hrow[r][c] = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint8_t* px = row + (size_t)tx.idx[k] * C;
 #pragma unroll
-            for (int c = 0; c < C; ++c) h[c] += (int)__ldg(px + c) * tx.w[k];
+            for (int c = 0; c < C; ++c) hrow[r][c] += (int)__ldg(px + c) * tx.w[k];
         }
-#pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] += (long long)h[c] * ty.w[r];
     }
+    // vertical pass.  OpenCV (resize.cpp, VResizeCubicVec_32s8u at the SSE baseline) evaluates the first 8 * floor(n / 8)
+    // elements of a row of n = dst_w * channels ints in fp32 -- S0*b0 + (S1*b1 + (S2*b2 + S3*b3)), b = beta * 2^-22, every
+    // product and sum rounded, round-half-even -- and the tail of the row in integers: (sum + 2^21) >> 22.
+    const int n_vec = (dst_w * C) & ~7;
+    const float b0 = (float)ty.w[0] * 0x1p-22f, b1 = (float)ty.w[1] * 0x1p-22f, b2 = (float)ty.w[2] * 0x1p-22f, b3 = (float)ty.w[3] * 0x1p-22f;
     uint8_t* o = dst + ((size_t)blockIdx.z * dst_h * dst_w + (size_t)dy * dst_w + dx) * C;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const long long v = (acc[c] + (1ll << 21)) >> 22;
-        o[c] = (uint8_t)max(0ll, min(255ll, v));
+        int v;
+        if (dx * C + c < n_vec) {
+            float acc = __fmul_rn((float)hrow[3][c], b3);
+            acc = __fadd_rn(__fmul_rn((float)hrow[2][c], b2), acc);
+            acc = __fadd_rn(__fmul_rn((float)hrow[1][c], b1), acc);
+            acc = __fadd_rn(__fmul_rn((float)hrow[0][c], b0), acc);
+            v = __float2int_rn(acc);
+        } else {
+            long long a = 0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) a += (long long)hrow[r][c] * ty.w[r];
+            v = (int)((a + (1ll << 21)) >> 22);
+        }
+        o[c] = (uint8_t)max(0, min(255, v));
     }
 }
 

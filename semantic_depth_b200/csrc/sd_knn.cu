@@ -488,6 +488,10 @@ __device__ __forceinline__ void flush_stats(GridState* gs, U128 acc_sum, U128 ac
 constexpr int kHeavy = SD_KNN_HEAVY;            // a disc with more candidates than this is swept by the whole warp
 constexpr int kExtreme = 4096;                  // ... and beyond this it goes to knn_heavy_kernel (3-D cell pruning, exact re-bounding)
 
+#ifndef SD_KNN_CLAIM
+#define SD_KNN_CLAIM 1      // a warp claims 32 * SD_KNN_CLAIM consecutive cell-sorted queries and works through them chunk by chunk
+#endif
+constexpr int kClaim = SD_KNN_CLAIM;
 #ifndef SD_KNN_WAVES
 #define SD_KNN_WAVES 16     // CTAs launched per SM (4 are resident; CTAs claim work until the queue is empty)
 #endif
@@ -515,9 +519,12 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
     unsigned long long acc_pos = 0ull;
     // warps claim 32 consecutive (cell-sorted) queries at a time from a per-job counter
     while (true) {
-        int wbase = 0;
-        if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
-        wbase = __shfl_sync(SD_FULL, wbase, 0);
+      int cbase = 0;
+      if (lane_id() == 0) cbase = atomicAdd(&J.gs->work, 32 * kClaim);
+      cbase = __shfl_sync(SD_FULL, cbase, 0);
+      if (cbase >= g.n) break;
+      for (int sub = 0; sub < kClaim; ++sub) {
+        const int wbase = cbase + 32 * sub;
         if (wbase >= g.n) break;
         const bool valid = wbase + lane_id() < g.n;              // lanes past the end shadow the last query (warp stays converged)
         const int i = valid ? wbase + lane_id() : g.n - 1;
@@ -755,6 +762,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
         const double avg = (keff > 0) ? sum / (double)keff : -1.0;
         if (valid) J.avg[__float_as_int(qp.w)] = avg;
         if (valid && avg > 0.0) { acc_sum = add128(acc_sum, to_fixed70(avg)); acc_sq = add128(acc_sq, to_fixed70(avg * avg)); ++acc_pos; }
+      }
     }
 
     // ---- partial cloud statistics (exact integer sums); knn_heavy_kernel adds its queries and finalises
@@ -1013,9 +1021,12 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
 #pragma unroll
     for (int l = 1; l < kLevels; ++l) if (g.cell * (double)(1 << (2 * l)) <= 0.25 * r) Lmax = l;   // measured: ~8 rows of small cells beat 3 rows of big ones
     while (true) {
-        int wbase = 0;
-        if (lane_id() == 0) wbase = atomicAdd(&J.gs->work, 32);
-        wbase = __shfl_sync(SD_FULL, wbase, 0);
+      int cbase = 0;
+      if (lane_id() == 0) cbase = atomicAdd(&J.gs->work, 32 * kClaim);
+      cbase = __shfl_sync(SD_FULL, cbase, 0);
+      if (cbase >= g.n) break;
+      for (int sub = 0; sub < kClaim; ++sub) {
+        const int wbase = cbase + 32 * sub;
         if (wbase >= g.n) break;
         const int i = wbase + lane_id();
         if (i >= g.n) continue;
@@ -1119,6 +1130,7 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
             }
         }
         J.cnt[__float_as_int(qp.w)] = (cap >= 0 && count > cap) ? cap + 1 : count;
+      }
     }
     if (lane_id() == 0) {
         __threadfence();

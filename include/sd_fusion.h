@@ -300,6 +300,29 @@ int sd_fuse_frames_host(const float* h_logits, const float* h_disp, int batch, i
                         float* d_logits_stage, float* d_disp_stage, SdFrameResult* d_results,
                         SdFrameResult* h_results, SdWorkspace* ws, void* stream);
 
+/* ---- FCN-8s decoder head (the producer side of the score-map mode) ------------------------------ */
+/* fcn8s/fcn.py:159-205 (`layers` up to second_skip): three 1x1 convolutions of the VGG feature maps to 3 classes, two
+ * 4x4 / stride-2 transposed convolutions and the two skip additions.  Its output is the `d_scores` input of
+ * sd_fuse_frames_scores / sd_pixel_fuse_scores, whose label kernel evaluates the last layer (fcn.py:207-213) itself.
+ *   d_layer3 [B][h8][w8][c3], d_layer4 [B][h8/2][w8/2][c4], d_layer7 [B][h8/4][w8/4][c7]  fp32 NHWC (vgg_layer3/4/7_out,
+ *   fcn.py:95-103; 256 / 512 / 4096 channels in VGG16);  weights in TF layouts: conv*_w [c][3] (kernel [1][1][in][out]),
+ *   deconv*_w [4][4][3 out][3 in]; biases [3];  d_scores [B][h8][w8][3] receives second_skip.
+ * Arithmetic contract (TensorFlow's summation order is not reproducible): fp32, no FMA; a 1x1 convolution sums the
+ * channels l, l+32, l+64, ... per lane l from 0.0, combines the 32 lanes by the xor tree 16, 8, 4, 2, 1 and adds the bias
+ * last; a transposed convolution accumulates (input row, input column, input channel) ascending from 0.0, then bias,
+ * then the skip tensor.  d_scratch: sd_fcn8s_head_scratch_bytes(batch, h8, w8) bytes of device memory. */
+typedef struct SdFcnHeadWeights {
+    const float* conv3_w; const float* conv3_b;
+    const float* conv4_w; const float* conv4_b;
+    const float* conv7_w; const float* conv7_b;
+    const float* deconv1_w; const float* deconv1_b;
+    const float* deconv2_w; const float* deconv2_b;
+} SdFcnHeadWeights;
+size_t sd_fcn8s_head_scratch_bytes(int batch, int h8, int w8);
+int sd_fcn8s_head(const float* d_layer3, const float* d_layer4, const float* d_layer7, int batch, int h8, int w8,
+                  int c3, int c4, int c7, const SdFcnHeadWeights* weights, float* d_scratch, size_t scratch_bytes,
+                  float* d_scores, void* stream);
+
 /* Optional device-side timing of the fused call: when enabled, sd_fuse_frames records CUDA events on
  * `stream` before / after the pixel-stage kernel and after the last kernel (skipped while the stream is
  * being captured into a CUDA graph).  sd_ws_stage_elapsed_ms: which = 0 pixel-stage kernel,

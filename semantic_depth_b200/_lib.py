@@ -57,6 +57,11 @@ class SdFrameResult(C.Structure):
     ]
 
 
+class SdFcnHeadWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("conv3_w", "conv3_b", "conv4_w", "conv4_b", "conv7_w", "conv7_b",
+                                         "deconv1_w", "deconv1_b", "deconv2_w", "deconv2_b")]
+
+
 class SdPredicate(C.Structure):
     _fields_ = [
         ("kind", C.c_int32), ("axis", C.c_int32), ("ia", C.c_int32), ("use_f32", C.c_int32),
@@ -102,6 +107,8 @@ SIGNATURES = {
     "sd_ws_set_stage_mask": (_I, [_P, _I]),
     "sd_ws_stage_elapsed_ms": (_I, [_P, _I, C.POINTER(C.c_float)]),
     "sd_ws_stage_times": (_I, [_P, C.POINTER(C.c_float)]),
+    "sd_fcn8s_head_scratch_bytes": (C.c_size_t, [_I, _I, _I]),
+    "sd_fcn8s_head": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(SdFcnHeadWeights), _P, C.c_size_t, _P, _P]),
     "sd_ws_cloud": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sd_ws_stage_src": (_I, [_P, _I, _I, C.POINTER(_P)]),
 }

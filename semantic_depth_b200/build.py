@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsd_fusion.so")
-SOURCES = ["sd_api.cu", "sd_pixel.cu", "sd_select.cu", "sd_compact.cu", "sd_plane.cu", "sd_knn.cu", "sd_ransac.cu", "sd_resize.cu", "sd_ply.cu", "sd_overlay.cu"]
+SOURCES = ["sd_api.cu", "sd_pixel.cu", "sd_select.cu", "sd_compact.cu", "sd_plane.cu", "sd_knn.cu", "sd_ransac.cu", "sd_resize.cu", "sd_ply.cu", "sd_overlay.cu", "sd_fcn_head.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -907,7 +907,7 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     if (P->use_sor) n += 2;                      // k-NN: main kernel + heavy queries
     if (P->use_ror) n += 2;                      // statistical filter applied to the sorted copies + per-cell statistics, radius search
     n += 1 + 1;                                  // final road compaction, slab
-    if (P->approach_both) n += 2 * sel + 1 + 1 + 1 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain
+    if (P->approach_both) n += 2 * sel + 1 + 1 + 2 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain (np.mean = leaf sums + tree)
     n += 1;                                      // finalize
     return n;
 }
@@ -927,6 +927,33 @@ extern "C" int sd_fuse_frames_host(const float* h_logits, const float* h_disp, i
     SD_CUDA_TRY(cudaMemcpyAsync(h_results, d_results, sizeof(SdFrameResult) * batch, cudaMemcpyDeviceToHost, st));
     SD_CUDA_TRY(cudaStreamSynchronize(st));
     return SD_OK;
+}
+
+int sd_launch_fcn_head(const float* l3, const float* l4, const float* l7, int batch, int h, int w, int c3, int c4, int c7,
+                       const float* w3, const float* b3, const float* w4, const float* b4, const float* w7, const float* b7,
+                       const float* wd1, const float* bd1, const float* wd2, const float* bd2,
+                       float* s7, float* s4, float* s3, float* first_skip, float* second_skip, cudaStream_t st);
+
+extern "C" size_t sd_fcn8s_head_scratch_bytes(int batch, int h8, int w8) {
+    if (batch < 1 || h8 < 4 || w8 < 4 || (h8 % 4) || (w8 % 4)) return 0;
+    const size_t n3 = (size_t)batch * h8 * w8;
+    return sizeof(float) * 3 * (n3 / 16 + n3 / 4 + n3 + n3 / 4);        // conv_1x1_of_7, _of_4, _of_3, first_skip
+}
+
+extern "C" int sd_fcn8s_head(const float* d_layer3, const float* d_layer4, const float* d_layer7, int batch, int h8, int w8,
+                             int c3, int c4, int c7, const SdFcnHeadWeights* w, float* d_scratch, size_t scratch_bytes,
+                             float* d_scores, void* stream) {
+    if (!d_layer3 || !d_layer4 || !d_layer7 || !w || !d_scratch || !d_scores) return fail(SD_ERR_INVALID, "sd_fcn8s_head: null argument");
+    if (!w->conv3_w || !w->conv3_b || !w->conv4_w || !w->conv4_b || !w->conv7_w || !w->conv7_b || !w->deconv1_w || !w->deconv1_b ||
+        !w->deconv2_w || !w->deconv2_b) return fail(SD_ERR_INVALID, "sd_fcn8s_head: null weight pointer");
+    const size_t need = sd_fcn8s_head_scratch_bytes(batch, h8, w8);
+    if (need == 0 || c3 < 1 || c4 < 1 || c7 < 1) return fail(SD_ERR_INVALID, "sd_fcn8s_head: the 1/8 map must be a multiple of 4 in both directions");
+    if (scratch_bytes < need) return fail(SD_ERR_WORKSPACE, "sd_fcn8s_head: scratch too small (sd_fcn8s_head_scratch_bytes)");
+    const size_t n3 = (size_t)batch * h8 * w8;
+    float* s7 = d_scratch; float* s4 = s7 + 3 * (n3 / 16); float* s3 = s4 + 3 * (n3 / 4); float* fs = s3 + 3 * n3;
+    return sd_launch_fcn_head(d_layer3, d_layer4, d_layer7, batch, h8, w8, c3, c4, c7, w->conv3_w, w->conv3_b, w->conv4_w, w->conv4_b,
+                              w->conv7_w, w->conv7_b, w->deconv1_w, w->deconv1_b, w->deconv2_w, w->deconv2_b, s7, s4, s3, fs, d_scores,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int sd_ws_enable_timing(SdWorkspace* ws, int enable) {

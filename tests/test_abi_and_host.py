@@ -162,7 +162,7 @@ def test_header_is_plain_c_and_layouts_match_field_by_field(tmp_path):
     if gcc is None:
         pytest.skip("gcc not available")
     structs = {"SdCamera": _lib.SdCamera, "SdParams": _lib.SdParams, "SdFrameResult": _lib.SdFrameResult,
-               "SdPredicate": _lib.SdPredicate}
+               "SdPredicate": _lib.SdPredicate, "SdFcnHeadWeights": _lib.SdFcnHeadWeights}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sd_fusion.h"', "int main(void) {"]
     for cname, ctype in structs.items():
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')

@@ -67,7 +67,7 @@ def test_head_feeds_the_fused_path(cuda_device):
         l4s.append(rng.standard_normal((h // 2, w // 2, channels[1]), dtype=np.float32) * np.float32(0.1))
         l7s.append(rng.standard_normal((h // 4, w // 4, channels[2]), dtype=np.float32) * np.float32(0.1))
         disps.append(disp); ups = (upw, upb)
-    l3, l4, l7, disp = (np.stack(v) for v in (l3s, l4s, l7s, disps))
+    l3, l4, l7, disp = (np.ascontiguousarray(np.stack(v)) for v in (l3s, l4s, l7s, disps))
     scores = head(torch.from_numpy(l3).cuda(), torch.from_numpy(l4).cuda(), torch.from_numpy(l7).cuda())
     want_scores = fcn_ref.fcn8s_head(l3, l4, l7, wts)
     assert np.array_equal(scores.cpu().numpy(), want_scores)

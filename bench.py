@@ -624,10 +624,12 @@ def run_stream(a, rank, world, dev, dev_index, device_map, P, intr, barrier, max
             d_logits.append(torch.from_numpy(lg).to(dev)); d_disp.append(torch.from_numpy(dp).to(dev))
     pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=False)
     if d_logits:                                            # warm: job tables + one graph per slot and batch shape
-        for _ in range(max(a.warmup, 1)):
-            pipe.warm_device(d_logits[0], d_disp[0], intr, tag=0)
+        for _ in range(max(a.warmup, 1) * len(pipe.slots)):
+            pipe.submit_device_stream(d_logits[0], d_disp[0], intr, tag=0)
         if d_logits[-1].shape[0] != B:
-            pipe.warm_device(d_logits[-1], d_disp[-1], intr, tag=0)
+            for _ in range(len(pipe.slots)):
+                pipe.submit_device_stream(d_logits[-1], d_disp[-1], intr, tag=0)
+        pipe.drain()
     main = torch.cuda.current_stream()
     sampler = ClockSampler(nvml_index(dev_index))
     sampler.start()
@@ -638,7 +640,7 @@ def run_stream(a, rank, world, dev, dev_index, device_map, P, intr, barrier, max
         s.stream.wait_event(t0)
     results = {}
     for k in range(len(starts)):
-        fin = pipe.submit_device(d_logits[k], d_disp[k], intr, tag=k)
+        fin = pipe.submit_device_stream(d_logits[k], d_disp[k], intr, tag=k)     # every batch lives at its own address
         if fin:
             results[fin[0]] = fin[1]
     for tag, res in pipe.drain():

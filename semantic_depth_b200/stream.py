@@ -184,6 +184,42 @@ class FramePipeline:
             self._launch(slot, logits, disp, intr, key=(logits.data_ptr(), disp.data_ptr(), logits.shape[0], _cam_key(intr)))
         return finished
 
+    def submit_device_stream(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, tag=None):
+        """Device inputs that live at a DIFFERENT address every batch (a stream of frames produced on the GPU): the pixel
+        stage -- the only kernels that see the input pointers -- is launched eagerly, everything behind it replays one
+        CUDA graph per slot and batch size.  No per-batch capture, no staging copy."""
+        slot, finished = self._take_slot()
+        eng = slot.engine
+        b = logits.shape[0]
+        with torch.cuda.stream(slot.stream):
+            slot.tag = tag
+            key = ("rest", b, _cam_key(intr))
+            g = slot.graphs.get(key) if self.use_graphs else None
+            slot.ev[0].record(slot.stream)
+            if self.use_graphs and g is None:
+                eng.enqueue(logits, disp, intr, self.params)              # eager once: builds the job tables (and is this batch's run)
+                slot.stream.synchronize()
+                eng.set_stage_mask(14)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=slot.stream):
+                    eng.enqueue(logits, disp, intr, self.params)
+                eng.set_stage_mask(15)
+                slot.graphs[key] = g
+            elif g is not None:
+                eng.set_stage_mask(1)
+                eng.enqueue(logits, disp, intr, self.params)              # pixel stage, eager: three launches
+                eng.set_stage_mask(15)
+                g.replay()
+            else:
+                eng.enqueue(logits, disp, intr, self.params)
+            slot.ev[4].record(slot.stream)
+            slot.nbytes = b * C.sizeof(SdFrameResult)
+            slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
+            slot.done.record(slot.stream)
+            slot.busy = True
+            slot.timed_total = True
+        return finished
+
     def warm_device(self, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, tag=None):
         """Run one batch through EVERY slot (captures each slot's graph for these tensors); returns the results."""
         out = []

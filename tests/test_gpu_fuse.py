@@ -150,6 +150,37 @@ def test_pipeline_slot_sees_every_camera(cuda_device):
     pipe.close()
 
 
+def test_pipeline_stream_submission_matches_cached_graph(cuda_device):
+    """A stream of batches that each live at their own device address (no per-batch graph capture: eager pixel stage + one
+    replayed graph for the rest) gives the answers of the plain cached-graph path, batch for batch, including a short last batch."""
+    from semantic_depth_b200.stream import FramePipeline
+    h, w, B = 128, 256, 3
+    P = FusionParams()
+    batches = []
+    for k in range(5):
+        nfr = B if k < 4 else 2
+        lg, dp, intr = scene.make_batch(nfr, h, w, first_seed=50 + k * B)
+        batches.append((torch.from_numpy(lg).cuda(), torch.from_numpy(dp).cuda()))
+    ref = FramePipeline(h, w, B, slots=1, device=cuda_device, params=P)
+    want = []
+    for k, (dl, dd) in enumerate(batches):
+        ref.submit_device(dl, dd, intr, tag=k)
+        want += ref.drain()
+    ref.close()
+    pipe = FramePipeline(h, w, B, slots=2, device=cuda_device, params=P)
+    got = []
+    for rep in range(2):                                      # second pass: every slot replays its graph
+        for k, (dl, dd) in enumerate(batches):
+            fin = pipe.submit_device_stream(dl, dd, intr, tag=k)
+            if fin:
+                got.append(fin)
+        got += pipe.drain()
+    pipe.close()
+    assert [t for t, _ in got] == list(range(5)) * 2
+    for tag, res in got:
+        assert res.raw.tobytes() == want[tag][1].raw.tobytes(), tag
+
+
 @pytest.mark.parametrize("variant", ["rw_only", "no_sor", "no_ror", "no_filters", "depth20", "k16"])
 def test_fused_param_variants(cuda_device, variant):
     h, w = 256, 512

@@ -98,6 +98,21 @@ def _pred(kind, axis=0, **kw) -> SdPredicate:
     return p
 
 
+def _thr32(c: "_Cloud", thr: float, upper: bool = True) -> float:
+    """The fp32 constant whose comparison with the fp32 device column decides like NumPy does.
+
+    fp32 cloud: the Python threshold is a weak scalar and becomes ``np.float32(thr)`` (nearest).  fp64 cloud (the
+    reference's clouds after the Open3D round trip, semantic_depth.py:244): NumPy compares in double, and for an fp32-born
+    value ``x < thr``  <=>  ``x < (smallest fp32 >= thr)``; ``x > thr``  <=>  ``x > (largest fp32 <= thr)``."""
+    t = np.float32(thr)
+    if c.f64 and np.isfinite(t):
+        if upper and float(t) < float(thr):
+            t = np.nextafter(t, np.float32(np.inf))
+        elif not upper and float(t) > float(thr):
+            t = np.nextafter(t, np.float32(-np.inf))
+    return float(t)
+
+
 def _keep(c: _Cloud, pred: SdPredicate) -> torch.Tensor:
     idx, _ = c.eng.filter(c.x, c.y, c.z, pred, want_points=False)
     return idx
@@ -111,7 +126,7 @@ def remove_from_to(points3D, colors, axis, from_meter, to_meter):
     c = _Cloud(points3D)
     if c.n == 0:
         raise ValueError("min() arg is an empty sequence")          # pcl.py:33
-    k = _keep(c, _pred(_lib.PRED_LT, axis, fa=float(-to_meter)))
+    k = _keep(c, _pred(_lib.PRED_LT, axis, fa=_thr32(c, float(-to_meter))))
     return c.take(c.src, k), c.take(colors, k)
 
 
@@ -217,7 +232,7 @@ def planes_intersection_at_certain_depth(C_p1, C_p2, z):
 def threshold_complete(points3D, colors, axis, threshold=15.0):
     """pcl.py:240-250: keep rows with ``abs(p[axis]) < threshold``."""
     c = _Cloud(points3D)
-    k = _keep(c, _pred(_lib.PRED_ABS_LT, axis, fa=float(threshold)))
+    k = _keep(c, _pred(_lib.PRED_ABS_LT, axis, fa=_thr32(c, float(threshold))))
     return c.take(c.src, k), c.take(colors, k)
 
 

@@ -175,6 +175,25 @@ def test_end_points_of_segment_with_non_finite_rows(cuda_device):
     assert a[0].shape == b[0].shape == (0, 3) and a[1].shape == b[1].shape == (0, 3)
 
 
+def test_thresholds_on_float64_clouds_compare_in_double(cuda_device):
+    """After the Open3D round trip the reference's clouds are float64 (semantic_depth.py:244) and NumPy compares them with
+    the Python threshold in double: a value equal to fl32(0.7) = 0.699999988 is < 0.7, and -fl32(7.1) is > -7.1."""
+    lo, hi = np.float32(0.7), np.nextafter(np.float32(0.7), np.float32(1))
+    assert float(lo) < 0.7 < float(hi)
+    for dtype in (np.float64, np.float32):
+        pts = np.zeros((6, 3), dtype)
+        pts[:, 2] = [lo, hi, -lo, -hi, 0.5, 0.9]
+        cols = colors_for(pts)
+        want = pts[pcl_ref.keep_threshold_complete(pts, 2, 0.7)]
+        got, _ = pcl.threshold_complete(pts, cols, 2, 0.7)
+        assert same(got, want), (dtype, got[:, 2], want[:, 2])
+        t = np.float32(7.1)
+        pts[:, 2] = [-t, np.nextafter(-t, np.float32(0)), np.nextafter(-t, np.float32(-10)), -7.5, -6.0, 1.0]
+        want = pts[pcl_ref.keep_remove_from_to(pts, 2, 7.1)]
+        got, _ = pcl.remove_from_to(pts, cols, 2, 0.0, 7.1)
+        assert same(got, want), (dtype, got[:, 2], want[:, 2])
+
+
 def test_intersection_distance_line(cuda_device, vec):
     road = {"Cx": 0.01, "Cy": -1.0, "Cz": 0.002, "C": -1.5}
     left = {"Cx": -1.0, "Cy": 0.03, "Cz": 0.001, "C": -4.0}

@@ -182,7 +182,7 @@ def test_thresholds_on_float64_clouds_compare_in_double(cuda_device):
     assert float(lo) < 0.7 < float(hi)
     for dtype in (np.float64, np.float32):
         pts = np.zeros((6, 3), dtype)
-        pts[:, 2] = [lo, hi, -lo, -hi, 0.5, 0.9]
+        pts[:, 2] = [lo, hi, -lo, -hi, 0.5, np.float32(0.9)]          # float32-born values, as after the Open3D round trip
         cols = colors_for(pts)
         want = pts[pcl_ref.keep_threshold_complete(pts, 2, 0.7)]
         got, _ = pcl.threshold_complete(pts, cols, 2, 0.7)

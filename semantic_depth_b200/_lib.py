@@ -111,6 +111,7 @@ SIGNATURES = {
     "sd_fcn8s_head": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(SdFcnHeadWeights), _P, C.c_size_t, _P, _P]),
     "sd_ws_cloud": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     "sd_ws_stage_src": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "sd_ws_stage_alive": (_I, [_P, _I, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
 }
 
 _lib = None

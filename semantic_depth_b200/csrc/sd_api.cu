@@ -82,7 +82,7 @@ struct FusedTables {
     SelJob* sel_road_y_med; SelJob* sel_road_y_mad; SelJob* sel_road_x_med; SelJob* sel_road_x_mad;
     SelJob* sel_fence_y_med; SelJob* sel_fence_y_mad; SelJob* sel_side_x_med; SelJob* sel_side_x_mad;   // side: [2F]
     CompactJob* c_road_y; CompactJob* c_road_x; CompactJob* c_road_plane; CompactJob* c_road_final;
-    CompactJob* c_fence_y; CompactJob* c_fence_z; CompactJob* c_split; CompactJob* c_side_x; CompactJob* c_side_plane;
+    CompactJob* c_fence_y; CompactJob* c_split; CompactJob* c_side_x; CompactJob* c_side_plane;
     PlaneJob* p_road; PlaneJob* p_side;
     MeanJob* m_fence; SlabJob* s_road; KnnJob* k_road; FinalJob* fin;
     RansacJob* r_road; RansacJob* r_side;
@@ -97,6 +97,7 @@ struct WsPriv {
     SdCamera cam;
     double cell_scale;
     cudaEvent_t ev_t[3]; bool timing; int stage_mask;
+    bool lazy_road, lazy_side;        // the current tables keep the MAD filters of the road / side chains as alive bytes
     cudaEvent_t ev_s[SD_NUM_STAGES + 1]; bool stages_valid;     // stage boundaries of the last timed call (profiling mode)
 };
 
@@ -117,6 +118,7 @@ size_t carve_all(SdWorkspace* ws, Carver& c) {
     ws->partials = c.take<double>((size_t)F * kChains * kPlaneBlocks * kPlaneSums);
     ws->ptick = c.take<uint32_t>((size_t)F * kChains);
     ws->pflags = c.take<uint8_t>((size_t)F * ws->height * ws->width);
+    ws->cflags = c.take<uint8_t>((size_t)F * 4 * cap);          // alive bytes of the unmaterialised filters: road, left, right, fence
     ws->ptcounts = c.take<int32_t>((size_t)F * ws->pix_tiles * 4);
     ws->ptoffs = c.take<int32_t>((size_t)F * ws->pix_tiles * 2);
     ws->lmask = c.take<double>(ws->width); ws->rmask = c.take<double>(ws->width);
@@ -652,6 +654,8 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
     FusedTables& T = pv->t;
     memset(&T, 0, sizeof(T));
     const int cap = ws->cap;
+    const bool lazy_road = (hyp_road == nullptr), lazy_side = (hyp_left == nullptr && hyp_right == nullptr);
+    pv->lazy_road = lazy_road; pv->lazy_side = lazy_side;
 #define SD_ALLOC(field, type, count) type* h_##field = jb.alloc<type>(count, &T.field); if (!h_##field) return fail(SD_ERR_WORKSPACE, "job arena too small")
     SD_ALLOC(sel_road_y_med, SelJob, B); SD_ALLOC(sel_road_y_mad, SelJob, B);
     SD_ALLOC(sel_road_x_med, SelJob, B); SD_ALLOC(sel_road_x_mad, SelJob, B);
@@ -659,7 +663,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
     SD_ALLOC(sel_side_x_med, SelJob, 2 * B); SD_ALLOC(sel_side_x_mad, SelJob, 2 * B);
     SD_ALLOC(c_road_y, CompactJob, B); SD_ALLOC(c_road_x, CompactJob, B);
     SD_ALLOC(c_road_plane, CompactJob, B); SD_ALLOC(c_road_final, CompactJob, B);
-    SD_ALLOC(c_fence_y, CompactJob, B); SD_ALLOC(c_fence_z, CompactJob, B);
+    SD_ALLOC(c_fence_y, CompactJob, B);
     SD_ALLOC(c_split, CompactJob, 2 * B); SD_ALLOC(c_side_x, CompactJob, 2 * B); SD_ALLOC(c_side_plane, CompactJob, 2 * B);
     SD_ALLOC(p_road, PlaneJob, B); SD_ALLOC(p_side, PlaneJob, 2 * B);
     SD_ALLOC(m_fence, MeanJob, B); SD_ALLOC(s_road, SlabJob, B); SD_ALLOC(k_road, KnnJob, B); SD_ALLOC(fin, FinalJob, B);
@@ -673,9 +677,35 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
         SdCloudBuf lA = frame_buf(ws->left[0], f, cap), lB = frame_buf(ws->left[1], f, cap);
         SdCloudBuf gA = frame_buf(ws->right[0], f, cap), gB = frame_buf(ws->right[1], f, cap);
         // ---------------- road chain ----------------
-        // MAD y (thr 15): rA (after the z cut) -> rB                       semantic_depth.py:209
+        // Without RANSAC hypotheses (the reference's behaviour) the three filters that precede the Open3D pair are NOT
+        // materialised one by one: MAD y is evaluated by the first pass of the x median (alive bytes + count), MAD x by the
+        // plane-moment kernel, and ONE compaction applies (alive && plane residual).  Three compactions of a cloud that keeps
+        // > 99 % of its points become one; counts and kept indices are what three separate calls give.  With hypotheses the
+        // triplets index rows of the filtered cloud, so that cloud has to exist: the classic layout below.
+        uint8_t* rflag = ws->cflags + ((size_t)f * 4 + 0) * cap;
+        uint8_t* lflag = ws->cflags + ((size_t)f * 4 + 1) * cap;
+        uint8_t* gflag = ws->cflags + ((size_t)f * 4 + 2) * cap;
+        uint8_t* fflag = ws->cflags + ((size_t)f * 4 + 3) * cap;
+        // MAD y (thr 15) on rA (after the z cut)                           semantic_depth.py:209
         fill_sel(h_sel_road_y_med[f], rA.y, &fs->n[SD_CNT_ROAD_Z], nullptr, &fs->med[0], ws, f, 0, nullptr, 0);
         fill_sel(h_sel_road_y_mad[f], rA.y, &fs->n[SD_CNT_ROAD_Z], &fs->med[0], &fs->mad[0], ws, f, 0, &fs->status, SD_ST_MAD_ZERO);
+        if (lazy_road) {
+            // MAD x (thr 2) on the survivors of MAD y                      :212
+            fill_sel(h_sel_road_x_med[f], rA.x, &fs->n[SD_CNT_ROAD_MAD_Y], nullptr, &fs->med[1], ws, f, 0, nullptr, 0);
+            h_sel_road_x_med[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_sel_road_x_med[f].flag = rflag;
+            h_sel_road_x_med[f].mark = MadMark{rA.y, &fs->med[0], &fs->mad[0], P.road_mad_y_thr, 0};
+            h_sel_road_x_med[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_Y];
+            fill_sel(h_sel_road_x_mad[f], rA.x, &fs->n[SD_CNT_ROAD_MAD_Y], &fs->med[1], &fs->mad[1], ws, f, 0, &fs->status, SD_ST_MAD_ZERO);
+            h_sel_road_x_mad[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_sel_road_x_mad[f].flag = rflag;
+            // plane (axis 1, thr 5) on the survivors of MAD x: rA -> rB    :215-219
+            fill_plane(h_p_road[f], rA, &fs->n[SD_CNT_ROAD_MAD_X], 1, fs->coeff[0], ws, f, 0, &fs->status, SD_ST_EMPTY_ROAD);
+            h_p_road[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_p_road[f].flag = rflag;
+            h_p_road[f].mark = MadMark{rA.x, &fs->med[1], &fs->mad[1], P.road_mad_x_thr, 0};
+            h_p_road[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_X];
+            { PredDev p = make_pred(SD_PRED_PLANE, 1); p.da = P.road_plane_thr; p.p_d = fs->coeff[0];
+              fill_compact(h_c_road_plane[f], rA, &fs->n[SD_CNT_ROAD_Z], rB, &fs->n[SD_CNT_ROAD_PLANE], p, ws, f, 0);
+              h_c_road_plane[f].flag = rflag; }
+        } else {
         { PredDev p = make_pred(SD_PRED_MAD, 1); p.fa = P.road_mad_y_thr; p.p_f0 = &fs->med[0]; p.p_f1 = &fs->mad[0];
           fill_compact(h_c_road_y[f], rA, &fs->n[SD_CNT_ROAD_Z], rB, &fs->n[SD_CNT_ROAD_MAD_Y], p, ws, f, 0); }
         // MAD x (thr 2): rB -> rA                                          :212
@@ -687,6 +717,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
         fill_plane(h_p_road[f], rA, &fs->n[SD_CNT_ROAD_MAD_X], 1, fs->coeff[0], ws, f, 0, &fs->status, SD_ST_EMPTY_ROAD);
         { PredDev p = make_pred(SD_PRED_PLANE, 1); p.da = P.road_plane_thr; p.p_d = fs->coeff[0];
           fill_compact(h_c_road_plane[f], rA, &fs->n[SD_CNT_ROAD_MAD_X], rB, &fs->n[SD_CNT_ROAD_PLANE], p, ws, f, 0); }
+        }
         if (hyp_road) {
             RansacJob& r = h_r_road[f]; memset(&r, 0, sizeof(r));
             r.x = rA.x; r.y = rA.y; r.z = rA.z; r.n = &fs->n[SD_CNT_ROAD_MAD_X];
@@ -711,25 +742,42 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
           s.lo32 = (float)P.slab_lo; s.hi32 = (float)P.slab_hi; s.use_f32 = 0;   // the cloud is fp64 after Open3D (:244)
           s.keys = fs->slab_keys; s.count = &fs->slab_count; }
         // ---------------- fence chain ----------------
-        // MAD y (thr 5): fA -> fB                                          :279
+        // MAD y (thr 5) and |z| < 35 in ONE compaction, fA -> fB: the second call sees the first one's survivors and the
+        // first call's count stays observable                              :279, :283-284
         fill_sel(h_sel_fence_y_med[f], fA.y, &fs->n[SD_CNT_FENCE_GATHER], nullptr, &fs->med[2], ws, f, 1, nullptr, 0);
         fill_sel(h_sel_fence_y_mad[f], fA.y, &fs->n[SD_CNT_FENCE_GATHER], &fs->med[2], &fs->mad[2], ws, f, 1, &fs->status, SD_ST_MAD_ZERO);
         { PredDev p = make_pred(SD_PRED_MAD, 1); p.fa = P.fence_mad_y_thr; p.p_f0 = &fs->med[2]; p.p_f1 = &fs->mad[2];
-          fill_compact(h_c_fence_y[f], fA, &fs->n[SD_CNT_FENCE_GATHER], fB, &fs->n[SD_CNT_FENCE_MAD_Y], p, ws, f, 1); }
-        // |z| < 35: fB -> fA                                               :283-284
-        { PredDev p = make_pred(SD_PRED_ABS_LT, 2); p.fa = P.fence_abs_z_thr;
-          fill_compact(h_c_fence_z[f], fB, &fs->n[SD_CNT_FENCE_MAD_Y], fA, &fs->n[SD_CNT_FENCE_ABS_Z], p, ws, f, 1); }
-        // mean x and the split: fA -> lA, gA                               :286-287
-        h_m_fence[f] = MeanJob{fA.x, &fs->n[SD_CNT_FENCE_ABS_Z], &fs->fence_mean, ws->mean_leaf + (size_t)f * (cap / 64 + 1)};
+          fill_compact(h_c_fence_y[f], fA, &fs->n[SD_CNT_FENCE_GATHER], fB, &fs->n[SD_CNT_FENCE_ABS_Z], p, ws, f, 1);
+          PredDev q = make_pred(SD_PRED_ABS_LT, 2); q.fa = P.fence_abs_z_thr;
+          h_c_fence_y[f].pred2 = q; h_c_fence_y[f].has_pred2 = 1; h_c_fence_y[f].n_mid = &fs->n[SD_CNT_FENCE_MAD_Y];
+          h_c_fence_y[f].mid_alive = fflag; }
+        // mean x and the split: fB -> lA, gA                               :286-287
+        h_m_fence[f] = MeanJob{fB.x, &fs->n[SD_CNT_FENCE_ABS_Z], &fs->fence_mean, ws->mean_leaf + (size_t)f * (cap / 64 + 1)};
         { PredDev p = make_pred(SD_PRED_LT, 0); p.p_f0 = &fs->fence_mean;
-          fill_compact(h_c_split[2 * f], fA, &fs->n[SD_CNT_FENCE_ABS_Z], lA, &fs->n[SD_CNT_LEFT_SPLIT], p, ws, f, 2); }
+          fill_compact(h_c_split[2 * f], fB, &fs->n[SD_CNT_FENCE_ABS_Z], lA, &fs->n[SD_CNT_LEFT_SPLIT], p, ws, f, 2); }
         { PredDev p = make_pred(SD_PRED_GT, 0); p.p_f0 = &fs->fence_mean;
-          fill_compact(h_c_split[2 * f + 1], fA, &fs->n[SD_CNT_FENCE_ABS_Z], gA, &fs->n[SD_CNT_RIGHT_SPLIT], p, ws, f, 3); }
-        // side MAD x: lA -> lB (thr 5), gA -> gB (thr 1)                   :291, :302
+          fill_compact(h_c_split[2 * f + 1], fB, &fs->n[SD_CNT_FENCE_ABS_Z], gA, &fs->n[SD_CNT_RIGHT_SPLIT], p, ws, f, 3); }
+        // side MAD x (thr 5 / 1) on lA / gA                                :291, :302
         fill_sel(h_sel_side_x_med[2 * f], lA.x, &fs->n[SD_CNT_LEFT_SPLIT], nullptr, &fs->med[3], ws, f, 2, nullptr, 0);
         fill_sel(h_sel_side_x_mad[2 * f], lA.x, &fs->n[SD_CNT_LEFT_SPLIT], &fs->med[3], &fs->mad[3], ws, f, 2, &fs->status, SD_ST_MAD_ZERO);
         fill_sel(h_sel_side_x_med[2 * f + 1], gA.x, &fs->n[SD_CNT_RIGHT_SPLIT], nullptr, &fs->med[4], ws, f, 3, nullptr, 0);
         fill_sel(h_sel_side_x_mad[2 * f + 1], gA.x, &fs->n[SD_CNT_RIGHT_SPLIT], &fs->med[4], &fs->mad[4], ws, f, 3, &fs->status, SD_ST_MAD_ZERO);
+        if (lazy_side) {
+            // the MAD filter is evaluated by the plane-moment kernel (alive bytes + count), one compaction applies
+            // (alive && plane residual): lA -> lB, gA -> gB                :294-298, :305-309
+            fill_plane(h_p_side[2 * f], lA, &fs->n[SD_CNT_LEFT_MAD_X], 0, fs->coeff[1], ws, f, 2, &fs->status, SD_ST_EMPTY_FENCE_LEFT);
+            h_p_side[2 * f].n_loop = &fs->n[SD_CNT_LEFT_SPLIT]; h_p_side[2 * f].flag = lflag;
+            h_p_side[2 * f].mark = MadMark{lA.x, &fs->med[3], &fs->mad[3], P.left_mad_x_thr, 0}; h_p_side[2 * f].n_mark_out = &fs->n[SD_CNT_LEFT_MAD_X];
+            fill_plane(h_p_side[2 * f + 1], gA, &fs->n[SD_CNT_RIGHT_MAD_X], 0, fs->coeff[2], ws, f, 3, &fs->status, SD_ST_EMPTY_FENCE_RIGHT);
+            h_p_side[2 * f + 1].n_loop = &fs->n[SD_CNT_RIGHT_SPLIT]; h_p_side[2 * f + 1].flag = gflag;
+            h_p_side[2 * f + 1].mark = MadMark{gA.x, &fs->med[4], &fs->mad[4], P.right_mad_x_thr, 0}; h_p_side[2 * f + 1].n_mark_out = &fs->n[SD_CNT_RIGHT_MAD_X];
+            { PredDev p = make_pred(SD_PRED_PLANE, 0); p.da = P.fence_plane_thr; p.p_d = fs->coeff[1];
+              fill_compact(h_c_side_plane[2 * f], lA, &fs->n[SD_CNT_LEFT_SPLIT], lB, &fs->n[SD_CNT_LEFT_PLANE], p, ws, f, 2);
+              h_c_side_plane[2 * f].flag = lflag; }
+            { PredDev p = make_pred(SD_PRED_PLANE, 0); p.da = P.fence_plane_thr; p.p_d = fs->coeff[2];
+              fill_compact(h_c_side_plane[2 * f + 1], gA, &fs->n[SD_CNT_RIGHT_SPLIT], gB, &fs->n[SD_CNT_RIGHT_PLANE], p, ws, f, 3);
+              h_c_side_plane[2 * f + 1].flag = gflag; }
+        } else {
         { PredDev p = make_pred(SD_PRED_MAD, 0); p.fa = P.left_mad_x_thr; p.p_f0 = &fs->med[3]; p.p_f1 = &fs->mad[3];
           fill_compact(h_c_side_x[2 * f], lA, &fs->n[SD_CNT_LEFT_SPLIT], lB, &fs->n[SD_CNT_LEFT_MAD_X], p, ws, f, 2); }
         { PredDev p = make_pred(SD_PRED_MAD, 0); p.fa = P.right_mad_x_thr; p.p_f0 = &fs->med[4]; p.p_f1 = &fs->mad[4];
@@ -741,6 +789,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
           fill_compact(h_c_side_plane[2 * f], lB, &fs->n[SD_CNT_LEFT_MAD_X], lA, &fs->n[SD_CNT_LEFT_PLANE], p, ws, f, 2); }
         { PredDev p = make_pred(SD_PRED_PLANE, 0); p.da = P.fence_plane_thr; p.p_d = fs->coeff[2];
           fill_compact(h_c_side_plane[2 * f + 1], gB, &fs->n[SD_CNT_RIGHT_MAD_X], gA, &fs->n[SD_CNT_RIGHT_PLANE], p, ws, f, 3); }
+        }
         for (int s = 0; s < 2; ++s) {
             const int32_t* hyp = s == 0 ? hyp_left : hyp_right;
             RansacJob& r = h_r_side[2 * f + s]; memset(&r, 0, sizeof(r));
@@ -830,10 +879,10 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
     if (do_pre) {
     SD_RUN(sd_launch_select_median(T.sel_road_y_med, B, cap, st));
     SD_RUN(sd_launch_select_median(T.sel_road_y_mad, B, cap, st));
-    SD_RUN(sd_launch_compact(T.c_road_y, B, cap, st));
+    if (!pv->lazy_road) SD_RUN(sd_launch_compact(T.c_road_y, B, cap, st));
     SD_RUN(sd_launch_select_median(T.sel_road_x_med, B, cap, st));
     SD_RUN(sd_launch_select_median(T.sel_road_x_mad, B, cap, st));
-    SD_RUN(sd_launch_compact(T.c_road_x, B, cap, st));
+    if (!pv->lazy_road) SD_RUN(sd_launch_compact(T.c_road_x, B, cap, st));
     SD_MARK(SD_STAGE_ROAD_MAD + 1);
     if (d_hyp_road) SD_RUN(sd_launch_ransac(T.r_road, B, cap, n_hyp, st));
     SD_RUN(sd_launch_plane(T.p_road, B, cap, st));
@@ -855,13 +904,12 @@ static int fuse_impl(const float* d_logits, const float* d_scores, const float* 
     if (do_pre && P.approach_both) {
         SD_RUN(sd_launch_select_median(T.sel_fence_y_med, B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_fence_y_mad, B, cap, sf));
-        SD_RUN(sd_launch_compact(T.c_fence_y, B, cap, sf));
-        SD_RUN(sd_launch_compact(T.c_fence_z, B, cap, sf));
+        SD_RUN(sd_launch_compact(T.c_fence_y, B, cap, sf));            // remove_noise_by_mad + threshold_complete
         SD_RUN(sd_launch_mean(T.m_fence, B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_split, 2 * B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_side_x_med, 2 * B, cap, sf));
         SD_RUN(sd_launch_select_median(T.sel_side_x_mad, 2 * B, cap, sf));
-        SD_RUN(sd_launch_compact(T.c_side_x, 2 * B, cap, sf));
+        if (!pv->lazy_side) SD_RUN(sd_launch_compact(T.c_side_x, 2 * B, cap, sf));
         if (d_hyp_left && d_hyp_right) SD_RUN(sd_launch_ransac(T.r_side, 2 * B, cap, n_hyp, sf));
         SD_RUN(sd_launch_plane(T.p_side, 2 * B, cap, sf));
         SD_RUN(sd_launch_compact(T.c_side_plane, 2 * B, cap, sf));
@@ -902,12 +950,12 @@ extern "C" int sd_fuse_kernel_count(const SdParams* P, int with_ransac) {
     if (!P) return 0;
     const int sel = 3, ransac = with_ransac ? 3 : 0;
     int n = 3;                                   // pixel stage: label, scan, scatter
-    n += 4 * sel + 2 + ransac + 1 + 1;           // road: 2 MADs (4 medians, 2 compactions), plane fit + filter
+    n += 4 * sel + (with_ransac ? 2 : 0) + ransac + 1 + 1;   // road: 2 MADs (4 medians; their compactions only with RANSAC), plane fit + filter
     if (P->use_sor || P->use_ror) n += 4;        // grid: bbox, count, scan, scatter
     if (P->use_sor) n += 2;                      // k-NN: main kernel + heavy queries
     if (P->use_ror) n += 2;                      // statistical filter applied to the sorted copies + per-cell statistics, radius search
     n += 1 + 1;                                  // final road compaction, slab
-    if (P->approach_both) n += 2 * sel + 1 + 1 + 2 + 1 + 2 * sel + 1 + ransac + 1 + 1;   // fence chain (np.mean = leaf sums + tree)
+    if (P->approach_both) n += 2 * sel + 1 + 2 + 1 + 2 * sel + (with_ransac ? 1 : 0) + ransac + 1 + 1;   // fence chain (MAD y + |z| in one compaction; np.mean = leaf sums + tree)
     n += 1;                                      // finalize
     return n;
 }
@@ -975,6 +1023,33 @@ extern "C" int sd_ws_stage_elapsed_ms(SdWorkspace* ws, int which, float* h_ms) {
     return SD_OK;
 }
 
+extern "C" int sd_ws_stage_alive(SdWorkspace* ws, int frame, int stage, const int32_t** d_src, const uint8_t** d_alive,
+                                 const int32_t** d_rows) {
+    if (!ws || !d_src || !d_alive || !d_rows || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_stage_alive: bad argument");
+    const WsPriv* pv = priv(ws);
+    const size_t cap = (size_t)ws->cap;
+    const FrameState* fs = ws->fs + frame;
+    switch (stage) {
+        case SD_CNT_ROAD_MAD_X:          // after the plane-moment kernel the road bytes hold MAD y && MAD x
+            if (!pv->lazy_road) break;
+            *d_src = ws->road[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 0) * cap; *d_rows = &fs->n[SD_CNT_ROAD_Z];
+            return SD_OK;
+        case SD_CNT_FENCE_MAD_Y:         // survivors of remove_noise_by_mad inside the fused MAD y + |z| compaction
+            *d_src = ws->fence[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 3) * cap; *d_rows = &fs->n[SD_CNT_FENCE_GATHER];
+            return SD_OK;
+        case SD_CNT_LEFT_MAD_X:
+            if (!pv->lazy_side) break;
+            *d_src = ws->left[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 1) * cap; *d_rows = &fs->n[SD_CNT_LEFT_SPLIT];
+            return SD_OK;
+        case SD_CNT_RIGHT_MAD_X:
+            if (!pv->lazy_side) break;
+            *d_src = ws->right[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 2) * cap; *d_rows = &fs->n[SD_CNT_RIGHT_SPLIT];
+            return SD_OK;
+        default: break;
+    }
+    return fail(SD_ERR_UNSUPPORTED, "sd_ws_stage_alive: this stage is either materialised (sd_ws_stage_src) or not retained");
+}
+
 extern "C" int sd_ws_stage_times(SdWorkspace* ws, float* h_ms) {
     if (!ws || !h_ms) return fail(SD_ERR_INVALID, "sd_ws_stage_times: null argument");
     WsPriv* pv = priv(ws);
@@ -986,7 +1061,9 @@ extern "C" int sd_ws_stage_times(SdWorkspace* ws, float* h_ms) {
 extern "C" int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const float** d_y, const float** d_z,
                            const int32_t** d_src, const int32_t** d_n) {
     if (!ws || frame < 0 || frame >= ws->max_frames || which < 0 || which > 2) return fail(SD_ERR_INVALID, "sd_ws_cloud: bad argument");
-    const SdCloudBuf& b = which == 0 ? ws->road[0] : (which == 1 ? ws->left[0] : ws->right[0]);
+    // the side chains end in their second buffer when the MAD filter was not materialised (one compaction instead of two)
+    const int side = priv(ws)->lazy_side ? 1 : 0;
+    const SdCloudBuf& b = which == 0 ? ws->road[0] : (which == 1 ? ws->left[side] : ws->right[side]);
     SdCloudBuf fb = frame_buf(b, frame, ws->cap);
     if (d_x) *d_x = fb.x; if (d_y) *d_y = fb.y; if (d_z) *d_z = fb.z; if (d_src) *d_src = fb.src;
     const int cnt = which == 0 ? SD_CNT_ROAD_ROR : (which == 1 ? SD_CNT_LEFT_PLANE : SD_CNT_RIGHT_PLANE);
@@ -998,17 +1075,19 @@ extern "C" int sd_ws_stage_src(SdWorkspace* ws, int frame, int stage, const int3
     if (!ws || !d_src || frame < 0 || frame >= ws->max_frames) return fail(SD_ERR_INVALID, "sd_ws_stage_src: bad argument");
     // buffers that still hold a stage's cloud when the fused call has finished
     const SdCloudBuf* b = nullptr;
+    const WsPriv* pv = priv(ws);
+    const int side = pv->lazy_side ? 1 : 0;
     switch (stage) {
         case SD_CNT_ROAD_ROR: b = &ws->road[0]; break;       // final road cloud
         case SD_CNT_ROAD_PLANE: b = &ws->road[1]; break;     // input of SOR/ROR
-        case SD_CNT_FENCE_ABS_Z: b = &ws->fence[0]; break;   // input of the split
-        case SD_CNT_FENCE_MAD_Y: b = &ws->fence[1]; break;
-        case SD_CNT_LEFT_PLANE: b = &ws->left[0]; break;
-        case SD_CNT_LEFT_MAD_X: b = &ws->left[1]; break;
-        case SD_CNT_RIGHT_PLANE: b = &ws->right[0]; break;
-        case SD_CNT_RIGHT_MAD_X: b = &ws->right[1]; break;
-        default: return fail(SD_ERR_UNSUPPORTED, "sd_ws_stage_src: stage cloud is not retained");
+        case SD_CNT_FENCE_ABS_Z: b = &ws->fence[1]; break;   // input of the split
+        case SD_CNT_LEFT_PLANE: b = &ws->left[side]; break;
+        case SD_CNT_RIGHT_PLANE: b = &ws->right[side]; break;
+        case SD_CNT_LEFT_MAD_X: if (!pv->lazy_side) b = &ws->left[1]; break;
+        case SD_CNT_RIGHT_MAD_X: if (!pv->lazy_side) b = &ws->right[1]; break;
+        default: break;
     }
+    if (!b) return fail(SD_ERR_UNSUPPORTED, "sd_ws_stage_src: stage cloud is not materialised (see sd_ws_stage_alive)");
     *d_src = b->src + (size_t)frame * ws->cap;
     return SD_OK;
 }

@@ -96,11 +96,15 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     const int tid = threadIdx.x;
     const int ntiles = ceil_div(n, kCompactTile);
     const PredRt P = resolve_pred(J.pred);
+    const bool two = J.has_pred2 != 0;
+    const PredRt P2 = two ? resolve_pred(J.pred2) : P;
+    const uint8_t* __restrict__ flag = J.flag;
+    int mid_local = 0;
     const float* __restrict__ X = J.x; const float* __restrict__ Y = J.y; const float* __restrict__ Z = J.z;
-    const bool need_x = (P.kind == SD_PRED_PLANE) || (J.ox != nullptr) || (P.axis == 0 && P.kind <= SD_PRED_GT);
-    const bool need_y = (P.kind == SD_PRED_PLANE) || (J.oy != nullptr) || (P.axis == 1 && P.kind <= SD_PRED_GT);
+    const bool need_x = (P.kind == SD_PRED_PLANE) || (J.ox != nullptr) || (P.axis == 0 && P.kind <= SD_PRED_GT) || (two && P2.axis == 0);
+    const bool need_y = (P.kind == SD_PRED_PLANE) || (J.oy != nullptr) || (P.axis == 1 && P.kind <= SD_PRED_GT) || (two && P2.axis == 1);
     const bool need_z = (P.kind == SD_PRED_PLANE) || (J.oz != nullptr) || (P.axis == 2 && P.kind <= SD_PRED_GT) ||
-                        (P.kind == SD_PRED_SLAB);
+                        (P.kind == SD_PRED_SLAB) || (two && P2.axis == 2);
     const bool need_s = (J.osrc != nullptr) && (J.src != nullptr);
 
     const bool vec_ok = ((((uintptr_t)X) | ((uintptr_t)Y) | ((uintptr_t)Z) | ((uintptr_t)J.src)) & 15) == 0;   // 128-bit loads need alignment
@@ -128,6 +132,12 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
             }
 #pragma unroll
             for (int k = 0; k < kCompactItems; ++k) keep |= eval_pred(P, x[k], y[k], z[k], base + k) ? (1u << k) : 0u;
+            if (flag) {
+                unsigned fm = 0u;
+#pragma unroll
+                for (int k = 0; k < kCompactItems; ++k) fm |= flag[base + k] ? (1u << k) : 0u;
+                keep &= fm;
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < kCompactItems; ++k) {
@@ -138,9 +148,19 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
                     if (need_y) y[k] = __ldg(Y + i);
                     if (need_z) z[k] = __ldg(Z + i);
                     if (need_s) sidx[k] = __ldg(J.src + i);
-                    keep |= eval_pred(P, x[k], y[k], z[k], i) ? (1u << k) : 0u;
+                    keep |= ((!flag || flag[i]) && eval_pred(P, x[k], y[k], z[k], i)) ? (1u << k) : 0u;
                 }
             }
+        }
+        if (two) {                                                  // the second reference call works on the first one's survivors
+            mid_local += __popc(keep);
+            if (J.mid_alive) {
+#pragma unroll
+                for (int k = 0; k < kCompactItems; ++k) if (base + k < n) J.mid_alive[base + k] = (uint8_t)((keep >> k) & 1u);
+            }
+#pragma unroll
+            for (int k = 0; k < kCompactItems; ++k)
+                if ((keep >> k) & 1u) { if (!eval_pred(P2, x[k], y[k], z[k], base + k)) keep &= ~(1u << k); }
         }
         int total;
         const int excl = block_excl_scan(__popc(keep), s_scan, &total);
@@ -165,7 +185,12 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
         }
         __syncthreads();   // s_tile / s_excl / staging are rewritten by the next iteration
     }
+    if (two) {                                                      // survivors of the first filter: exact integer sum
+        mid_local = warp_sum(mid_local);
+        if (lane_id() == 0 && mid_local) atomicAdd(&J.ctl->aux0, (unsigned)mid_local);
+    }
     if (scan_finish(J.ctl, J.status, max(ntiles, 0), gridDim.x)) {
+        if (tid == 0 && two) { if (J.n_mid) *J.n_mid = (int)__ldcg(&J.ctl->aux0); J.ctl->aux0 = 0u; }
         if (tid == 0) {
             int nout = (n > 0 && J.n_out) ? __ldcg(J.n_out) : 0;
             if (n <= 0 && J.n_out) *J.n_out = 0;

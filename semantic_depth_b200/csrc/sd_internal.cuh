@@ -48,12 +48,24 @@ struct SelState {
     uint32_t rank[2];           // remaining rank inside the prefix bucket
     uint32_t nan_count;
     uint32_t ticket;
-    uint32_t pad_[2];
+    uint32_t alive;             // marking jobs: rows that passed the mark predicate in pass 0 (self-cleaned after pass 2)
+    uint32_t pad_;
     uint32_t hist[2][kSelBins];
+};
+// A MAD filter that is not materialised by a compaction: the NEXT kernel over the cloud evaluates it on the fly, writes one
+// alive byte per row and counts the survivors (pcl.py:63-67: fl32(fl32(0.6745f * |c - med|) / mad) < thr).
+struct MadMark {
+    const float* col;           // nullptr: no marking
+    const float* med; const float* mad;
+    float thr; int32_t pad_;
 };
 struct SelJob {
     const float* col;
-    const int32_t* n;
+    const int32_t* n;           // number of keys that take part (alive rows).  Marking jobs: written by pass 0 (= n_mark_out)
+    const int32_t* n_loop;      // physical rows of the column when rows are masked (nullptr: *n)
+    uint8_t* flag;              // alive byte per row (nullptr: every row takes part); marking jobs write it in pass 0
+    MadMark mark;               // pass 0 evaluates this filter first, rows that fail never enter the histogram
+    int32_t* n_mark_out;        // marking jobs: where the survivor count goes
     const float* center;        // nullptr: keys are col[i]; else keys are |col[i] - *center|
     SelState* st;
     float* out;                 // the median
@@ -79,6 +91,12 @@ struct CompactJob {
     const float* x; const float* y; const float* z; const int32_t* src; const int32_t* n_in;
     float* ox; float* oy; float* oz; int32_t* osrc; int32_t* n_out;
     PredDev pred;
+    const uint8_t* flag;        // optional alive byte per input row (rows marked dead by earlier, unmaterialised filters)
+    PredDev pred2;              // optional second filter applied to the survivors of `pred` (has_pred2): two reference
+    int32_t has_pred2;          //   calls in one pass, e.g. remove_noise_by_mad + threshold_complete (semantic_depth.py:279,283)
+    int32_t pad2_;
+    int32_t* n_mid;             // has_pred2: survivors of flag && pred (the first call's count stays observable)
+    uint8_t* mid_alive;         // has_pred2, optional: one byte per input row, 1 = survived flag && pred (keeps that stage inspectable)
     unsigned long long* status; // look-back words, max_tiles long
     ScanCtl* ctl;
     uint32_t* frame_status;     // optional: OR `empty_bit` when the output is empty
@@ -89,6 +107,10 @@ struct CompactJob {
 // ---- plane fit -----------------------------------------------------------------------------------------
 struct PlaneJob {
     const float* x; const float* y; const float* z; const int32_t* n;
+    const int32_t* n_loop;      // physical rows when rows are masked (nullptr: *n)
+    uint8_t* flag;              // alive byte per row, read (nullptr: all alive) and, with `mark`, rewritten in place
+    MadMark mark;               // evaluate this MAD filter first (remove_noise_by_mad before the plane fit)
+    int32_t* n_mark_out;        // mark: survivor count
     int32_t axis;               // regressed coordinate (pcl.py axis argument)
     int32_t use_inliers;        // RANSAC refit: only points with |res(hyp)| < thr contribute
     const double* hyp;          // C0,C1,C2 of the best hypothesis (device)
@@ -243,6 +265,7 @@ struct SdWorkspace {
     uint32_t* ptick;                     // [F][4]
     // pixel pass
     uint8_t* pflags;                     // [F][H*W] per-pixel label / keep flags
+    uint8_t* cflags;                     // [F][4][cap] alive bytes of unmaterialised MAD filters: road, left, right, fence chain
     int32_t* ptcounts;                   // [F][pix_tiles][4]
     int32_t* ptoffs;                     // [F][pix_tiles][2]
     int pix_tiles;

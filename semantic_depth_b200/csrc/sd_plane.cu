@@ -25,11 +25,16 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
     __shared__ double s_part[kPlaneThreads / 32][kPlaneSums];
     __shared__ int s_last;
     const PlaneJob J = jobs[blockIdx.y];
-    const int n = *J.n;
+    // masked clouds: rows [0, n) exist, the alive ones (flag) take part; with `mark` the MAD filter that precedes the fit in
+    // the reference (remove_noise_by_mad, then remove_noise_by_fitting_plane) is evaluated here and the bytes rewritten
+    const bool marking = J.mark.col != nullptr;
+    const int n = J.n_loop ? *J.n_loop : *J.n;
     const int tid = threadIdx.x;
+    const float mk_med = marking ? *J.mark.med : 0.f, mk_mad = marking ? *J.mark.mad : 1.f;
+    uint8_t* __restrict__ flag = J.flag;
 
     float u0 = 0.f, v0 = 0.f, w0 = 0.f;
-    if (n > 0) pick_uvw(J.axis, __ldg(J.x), __ldg(J.y), __ldg(J.z), u0, v0, w0);
+    if (n > 0) pick_uvw(J.axis, __ldg(J.x), __ldg(J.y), __ldg(J.z), u0, v0, w0);      // any finite point of the cloud serves as the shift
     double h0 = 0, h1 = 0, h2 = 0;
     if (J.use_inliers) { h0 = J.hyp[0]; h1 = J.hyp[1]; h2 = J.hyp[2]; }
 
@@ -37,6 +42,14 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
 #pragma unroll
     for (int k = 0; k < kPlaneSums; ++k) s[k] = 0.0;
     for (int i = blockIdx.x * kPlaneThreads + tid; i < n; i += gridDim.x * kPlaneThreads) {
+        bool alive = flag ? (flag[i] != 0) : true;
+        if (marking) {
+            const float ad = fabsf(__ldg(J.mark.col + i) - mk_med);            // pcl.py:79
+            const float pen = (0.6745f * ad) / mk_mad;                          // pcl.py:63
+            alive = alive && (pen < J.mark.thr);                                // pcl.py:67
+            flag[i] = alive ? 1 : 0;
+        }
+        if (!alive) continue;
         float u, v, w;
         pick_uvw(J.axis, __ldg(J.x + i), __ldg(J.y + i), __ldg(J.z + i), u, v, w);
         if (J.use_inliers) {
@@ -79,6 +92,7 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
         *J.ticket = 0;
         const double Suu = s_tot[0], Suv = s_tot[1], Su = s_tot[2], Svv = s_tot[3], Sv = s_tot[4];
         const double Suw = s_tot[5], Svw = s_tot[6], Sw = s_tot[7], N = s_tot[8];
+        if (marking && J.n_mark_out) *J.n_mark_out = (int)N;                    // survivors of the MAD filter
         double c0, c1, c2;
         const double qnan = __longlong_as_double(0x7ff8000000000000ull);
         if (N < 1.0) {

@@ -42,11 +42,18 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     __shared__ int s_last;
 
     const SelJob job = jobs[blockIdx.y];
-    const int n = *job.n;
     SelState* st = job.st;
     const int tid = threadIdx.x;
     const bool absdev = job.center != nullptr;
     const float c = absdev ? *job.center : 0.f;
+    // masked columns: rows [0, n_it) exist, `n` of them are alive.  A marking job decides the alive bytes itself in pass 0
+    // (the MAD filter that precedes this median in the reference, pcl.py:46-81) and learns n at the end of that pass.
+    const bool marking = (PASS == 0) && (job.mark.col != nullptr);
+    const int n_it = job.n_loop ? *job.n_loop : *job.n;
+    int n = marking ? 0 : *job.n;
+    const float mk_med = job.mark.col ? *job.mark.med : 0.f, mk_mad = job.mark.col ? *job.mark.mad : 1.f;
+    uint8_t* __restrict__ flag = job.flag;
+    uint32_t alive_local = 0;
 
     uint32_t pre0 = 0, pre1 = 0;
     if (PASS > 0) { pre0 = st->prefix[0]; pre1 = st->prefix[1]; }
@@ -59,12 +66,22 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     // grid-stride over tiles of kSelThreads*kSelItems keys; run-length aggregated smem atomics
     const int tile = kSelThreads * kSelItems;
     uint32_t nan_local = 0;
-    for (int base = blockIdx.x * tile; base < n; base += gridDim.x * tile) {
+    for (int base = blockIdx.x * tile; base < n_it; base += gridDim.x * tile) {
         uint32_t run_d = 0xffffffffu, run_c = 0; int run_s = 0;
 #pragma unroll
         for (int k = 0; k < kSelItems; ++k) {
             int i = base + k * kSelThreads + tid;
-            if (i < n) {
+            bool alive = i < n_it;
+            if (alive && marking) {
+                const float ad = fabsf(__ldg(job.mark.col + i) - mk_med);      // abs(points1D - median)          pcl.py:79
+                const float pen = (0.6745f * ad) / mk_mad;                      // 0.6745 * abs_diffs / mad_axis   pcl.py:63
+                alive = pen < job.mark.thr;                                     // NaN / inf compare false         pcl.py:67
+                flag[i] = alive ? 1 : 0;
+                alive_local += alive ? 1u : 0u;
+            } else if (alive && flag) {
+                alive = flag[i] != 0;
+            }
+            if (alive) {
                 float val = sel_val(job.col, i, absdev, c);
                 uint32_t key = f2key(val);
                 if (PASS == 0) nan_local += (val != val) ? 1u : 0u;
@@ -92,6 +109,10 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
         if (two) { uint32_t h1 = s_hist[1][i]; if (h1) atomicAdd(&st->hist[1][i], h1); }
     }
     if (PASS == 0 && tid == 0 && s_nan) atomicAdd(&st->nan_count, s_nan);
+    if (marking) {
+        alive_local = (uint32_t)warp_sum((int)alive_local);
+        if (lane_id() == 0 && alive_local) atomicAdd(&st->alive, alive_local);
+    }
 
     // ---- last CTA of the job resolves the digit of both ranks
     __threadfence();
@@ -103,6 +124,10 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    if (marking) {
+        n = (int)__ldcg(&st->alive);
+        if (tid == 0 && job.n_mark_out) *job.n_mark_out = n;
+    }
 
     // copy the merged histogram(s) back to smem, zero the global copy
     for (int i = tid; i < NB; i += kSelThreads) {
@@ -148,7 +173,7 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
             else med = (a + b) * 0.5f;                 // np.mean of the two middle values, fp32
             *job.out = med;
             if (job.status && job.zero_bit && n > 0 && !(med > 0.0f)) atomicOr(job.status, job.zero_bit);
-            st->nan_count = 0;
+            st->nan_count = 0; st->alive = 0;
             st->prefix[0] = st->prefix[1] = 0; st->rank[0] = st->rank[1] = 0;
         }
     }

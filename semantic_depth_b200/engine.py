@@ -251,8 +251,20 @@ class FusionEngine:
     def stage_src(self, frame: int, stage: str, n: int) -> torch.Tensor:
         """Source pixel indices of a retained intermediate stage (parity tests)."""
         p = C.c_void_p()
-        check(self.lib.sd_ws_stage_src(self._ws, frame, _lib.COUNT_NAMES.index(stage), C.byref(p)), "sd_ws_stage_src")
-        return self._view(p.value, n, torch.int32).clone()
+        rc = self.lib.sd_ws_stage_src(self._ws, frame, _lib.COUNT_NAMES.index(stage), C.byref(p))
+        if rc == 0:
+            return self._view(p.value, n, torch.int32).clone()
+        # a filter that the fused path does not materialise (alive bytes over the chain's input): select the rows here
+        ps, pa, pr = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(self.lib.sd_ws_stage_alive(self._ws, frame, _lib.COUNT_NAMES.index(stage), C.byref(ps), C.byref(pa), C.byref(pr)),
+              "sd_ws_stage_alive")
+        rows = int(self._view(pr.value, 1, torch.int32).item())
+        src = self._view(ps.value, rows, torch.int32)
+        alive = self._view(pa.value, rows, torch.uint8)
+        out = src[alive != 0].clone()
+        if out.numel() != n:
+            raise _lib.SdError(f"stage {stage}: {out.numel()} alive rows, expected {n}")
+        return out
 
     def _view(self, ptr: int, n: int, dtype) -> torch.Tensor:
         """Tensor view of `n` elements at raw device address `ptr` inside the workspace."""

@@ -699,7 +699,7 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
             h_sel_road_x_mad[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_sel_road_x_mad[f].flag = rflag;
             // plane (axis 1, thr 5) on the survivors of MAD x: rA -> rB    :215-219
             fill_plane(h_p_road[f], rA, &fs->n[SD_CNT_ROAD_MAD_X], 1, fs->coeff[0], ws, f, 0, &fs->status, SD_ST_EMPTY_ROAD);
-            h_p_road[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_p_road[f].flag = rflag;
+            h_p_road[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_p_road[f].flag = rflag; h_p_road[f].flag_out = rflag;
             h_p_road[f].mark = MadMark{rA.x, &fs->med[1], &fs->mad[1], P.road_mad_x_thr, 0};
             h_p_road[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_X];
             { PredDev p = make_pred(SD_PRED_PLANE, 1); p.da = P.road_plane_thr; p.p_d = fs->coeff[0];
@@ -766,10 +766,10 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
             // the MAD filter is evaluated by the plane-moment kernel (alive bytes + count), one compaction applies
             // (alive && plane residual): lA -> lB, gA -> gB                :294-298, :305-309
             fill_plane(h_p_side[2 * f], lA, &fs->n[SD_CNT_LEFT_MAD_X], 0, fs->coeff[1], ws, f, 2, &fs->status, SD_ST_EMPTY_FENCE_LEFT);
-            h_p_side[2 * f].n_loop = &fs->n[SD_CNT_LEFT_SPLIT]; h_p_side[2 * f].flag = lflag;
+            h_p_side[2 * f].n_loop = &fs->n[SD_CNT_LEFT_SPLIT]; h_p_side[2 * f].flag_out = lflag;
             h_p_side[2 * f].mark = MadMark{lA.x, &fs->med[3], &fs->mad[3], P.left_mad_x_thr, 0}; h_p_side[2 * f].n_mark_out = &fs->n[SD_CNT_LEFT_MAD_X];
             fill_plane(h_p_side[2 * f + 1], gA, &fs->n[SD_CNT_RIGHT_MAD_X], 0, fs->coeff[2], ws, f, 3, &fs->status, SD_ST_EMPTY_FENCE_RIGHT);
-            h_p_side[2 * f + 1].n_loop = &fs->n[SD_CNT_RIGHT_SPLIT]; h_p_side[2 * f + 1].flag = gflag;
+            h_p_side[2 * f + 1].n_loop = &fs->n[SD_CNT_RIGHT_SPLIT]; h_p_side[2 * f + 1].flag_out = gflag;
             h_p_side[2 * f + 1].mark = MadMark{gA.x, &fs->med[4], &fs->mad[4], P.right_mad_x_thr, 0}; h_p_side[2 * f + 1].n_mark_out = &fs->n[SD_CNT_RIGHT_MAD_X];
             { PredDev p = make_pred(SD_PRED_PLANE, 0); p.da = P.fence_plane_thr; p.p_d = fs->coeff[1];
               fill_compact(h_c_side_plane[2 * f], lA, &fs->n[SD_CNT_LEFT_SPLIT], lB, &fs->n[SD_CNT_LEFT_PLANE], p, ws, f, 2);

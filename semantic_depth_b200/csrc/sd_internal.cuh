@@ -108,7 +108,8 @@ struct CompactJob {
 struct PlaneJob {
     const float* x; const float* y; const float* z; const int32_t* n;
     const int32_t* n_loop;      // physical rows when rows are masked (nullptr: *n)
-    uint8_t* flag;              // alive byte per row, read (nullptr: all alive) and, with `mark`, rewritten in place
+    const uint8_t* flag;        // alive byte per row from earlier unmaterialised filters (nullptr: all rows alive)
+    uint8_t* flag_out;          // with `mark`: alive byte per row after this filter (may alias `flag`: one thread per row)
     MadMark mark;               // evaluate this MAD filter first (remove_noise_by_mad before the plane fit)
     int32_t* n_mark_out;        // mark: survivor count
     int32_t axis;               // regressed coordinate (pcl.py axis argument)

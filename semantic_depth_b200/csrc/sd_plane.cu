@@ -31,7 +31,7 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
     const int n = J.n_loop ? *J.n_loop : *J.n;
     const int tid = threadIdx.x;
     const float mk_med = marking ? *J.mark.med : 0.f, mk_mad = marking ? *J.mark.mad : 1.f;
-    uint8_t* __restrict__ flag = J.flag;
+    const uint8_t* flag = J.flag;
 
     float u0 = 0.f, v0 = 0.f, w0 = 0.f;
     if (n > 0) pick_uvw(J.axis, __ldg(J.x), __ldg(J.y), __ldg(J.z), u0, v0, w0);      // any finite point of the cloud serves as the shift
@@ -47,7 +47,7 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
             const float ad = fabsf(__ldg(J.mark.col + i) - mk_med);            // pcl.py:79
             const float pen = (0.6745f * ad) / mk_mad;                          // pcl.py:63
             alive = alive && (pen < J.mark.thr);                                // pcl.py:67
-            flag[i] = alive ? 1 : 0;
+            J.flag_out[i] = alive ? 1 : 0;
         }
         if (!alive) continue;
         float u, v, w;

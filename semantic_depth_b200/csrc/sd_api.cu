@@ -694,14 +694,14 @@ int build_fused_tables(SdWorkspace* ws, int B, const SdParams& P, const SdCamera
             fill_sel(h_sel_road_x_med[f], rA.x, &fs->n[SD_CNT_ROAD_MAD_Y], nullptr, &fs->med[1], ws, f, 0, nullptr, 0);
             h_sel_road_x_med[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_sel_road_x_med[f].flag = rflag;
             h_sel_road_x_med[f].mark = MadMark{rA.y, &fs->med[0], &fs->mad[0], P.road_mad_y_thr, 0};
-            h_sel_road_x_med[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_Y];
+            h_sel_road_x_med[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_Y]; h_sel_road_x_med[f].first_alive_out = &fs->road_first_alive;
             fill_sel(h_sel_road_x_mad[f], rA.x, &fs->n[SD_CNT_ROAD_MAD_Y], &fs->med[1], &fs->mad[1], ws, f, 0, &fs->status, SD_ST_MAD_ZERO);
             h_sel_road_x_mad[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_sel_road_x_mad[f].flag = rflag;
             // plane (axis 1, thr 5) on the survivors of MAD x: rA -> rB    :215-219
             fill_plane(h_p_road[f], rA, &fs->n[SD_CNT_ROAD_MAD_X], 1, fs->coeff[0], ws, f, 0, &fs->status, SD_ST_EMPTY_ROAD);
             h_p_road[f].n_loop = &fs->n[SD_CNT_ROAD_Z]; h_p_road[f].flag = rflag; h_p_road[f].flag_out = rflag;
             h_p_road[f].mark = MadMark{rA.x, &fs->med[1], &fs->mad[1], P.road_mad_x_thr, 0};
-            h_p_road[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_X];
+            h_p_road[f].n_mark_out = &fs->n[SD_CNT_ROAD_MAD_X]; h_p_road[f].shift_row = &fs->road_first_alive;
             { PredDev p = make_pred(SD_PRED_PLANE, 1); p.da = P.road_plane_thr; p.p_d = fs->coeff[0];
               fill_compact(h_c_road_plane[f], rA, &fs->n[SD_CNT_ROAD_Z], rB, &fs->n[SD_CNT_ROAD_PLANE], p, ws, f, 0);
               h_c_road_plane[f].flag = rflag; }

@@ -39,7 +39,7 @@ struct FrameState {
     double coeff[3][3];         // road / left / right plane: C0, C1, C2 (regression form)
     double sor_stats[3];        // mean, std, threshold
     int32_t ransac_best[3];
-    int32_t pad2_;
+    int32_t road_first_alive;   // lowest row of the road cloud that survives MAD y (shift of the plane moments)
 };
 
 // ---- radix select ----------------------------------------------------------------------------------
@@ -49,7 +49,7 @@ struct SelState {
     uint32_t nan_count;
     uint32_t ticket;
     uint32_t alive;             // marking jobs: rows that passed the mark predicate in pass 0 (self-cleaned after pass 2)
-    uint32_t pad_;
+    uint32_t first_inv;         // marking jobs: 0xffffffff - (lowest alive row), 0 = none (atomicMax; self-cleaned)
     uint32_t hist[2][kSelBins];
 };
 // A MAD filter that is not materialised by a compaction: the NEXT kernel over the cloud evaluates it on the fly, writes one
@@ -66,6 +66,7 @@ struct SelJob {
     uint8_t* flag;              // alive byte per row (nullptr: every row takes part); marking jobs write it in pass 0
     MadMark mark;               // pass 0 evaluates this filter first, rows that fail never enter the histogram
     int32_t* n_mark_out;        // marking jobs: where the survivor count goes
+    int32_t* first_alive_out;   // marking jobs: lowest alive row (a finite representative of the surviving cloud), 0 if none
     const float* center;        // nullptr: keys are col[i]; else keys are |col[i] - *center|
     SelState* st;
     float* out;                 // the median
@@ -112,6 +113,7 @@ struct PlaneJob {
     uint8_t* flag_out;          // with `mark`: alive byte per row after this filter (may alias `flag`: one thread per row)
     MadMark mark;               // evaluate this MAD filter first (remove_noise_by_mad before the plane fit)
     int32_t* n_mark_out;        // mark: survivor count
+    const int32_t* shift_row;   // row whose coordinates shift the moments (nullptr: row 0); must be a finite row of the cloud
     int32_t axis;               // regressed coordinate (pcl.py axis argument)
     int32_t use_inliers;        // RANSAC refit: only points with |res(hyp)| < thr contribute
     const double* hyp;          // C0,C1,C2 of the best hypothesis (device)

@@ -34,7 +34,10 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
     const uint8_t* flag = J.flag;
 
     float u0 = 0.f, v0 = 0.f, w0 = 0.f;
-    if (n > 0) pick_uvw(J.axis, __ldg(J.x), __ldg(J.y), __ldg(J.z), u0, v0, w0);      // any finite point of the cloud serves as the shift
+    if (n > 0) {                                      // any finite point of the surviving cloud serves as the shift
+        const int r0 = J.shift_row ? min(max(*J.shift_row, 0), n - 1) : 0;
+        pick_uvw(J.axis, __ldg(J.x + r0), __ldg(J.y + r0), __ldg(J.z + r0), u0, v0, w0);
+    }
     double h0 = 0, h1 = 0, h2 = 0;
     if (J.use_inliers) { h0 = J.hyp[0]; h1 = J.hyp[1]; h2 = J.hyp[2]; }
 

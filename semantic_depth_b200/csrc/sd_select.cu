@@ -53,7 +53,7 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     int n = marking ? 0 : *job.n;
     const float mk_med = job.mark.col ? *job.mark.med : 0.f, mk_mad = job.mark.col ? *job.mark.mad : 1.f;
     uint8_t* __restrict__ flag = job.flag;
-    uint32_t alive_local = 0;
+    uint32_t alive_local = 0, first_local = 0;
 
     uint32_t pre0 = 0, pre1 = 0;
     if (PASS > 0) { pre0 = st->prefix[0]; pre1 = st->prefix[1]; }
@@ -78,6 +78,7 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
                 alive = pen < job.mark.thr;                                     // NaN / inf compare false         pcl.py:67
                 flag[i] = alive ? 1 : 0;
                 alive_local += alive ? 1u : 0u;
+                if (alive) first_local = max(first_local, 0xffffffffu - (uint32_t)i);
             } else if (alive && flag) {
                 alive = flag[i] != 0;
             }
@@ -112,6 +113,8 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     if (marking) {
         alive_local = (uint32_t)warp_sum((int)alive_local);
         if (lane_id() == 0 && alive_local) atomicAdd(&st->alive, alive_local);
+        first_local = warp_max(first_local);
+        if (lane_id() == 0 && first_local) atomicMax(&st->first_inv, first_local);
     }
 
     // ---- last CTA of the job resolves the digit of both ranks
@@ -127,6 +130,7 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
     if (marking) {
         n = (int)__ldcg(&st->alive);
         if (tid == 0 && job.n_mark_out) *job.n_mark_out = n;
+        if (tid == 0 && job.first_alive_out) { const uint32_t fi = __ldcg(&st->first_inv); *job.first_alive_out = fi ? (int)(0xffffffffu - fi) : 0; }
     }
 
     // copy the merged histogram(s) back to smem, zero the global copy
@@ -173,7 +177,7 @@ select_pass_kernel(const SelJob* __restrict__ jobs) {
             else med = (a + b) * 0.5f;                 // np.mean of the two middle values, fp32
             *job.out = med;
             if (job.status && job.zero_bit && n > 0 && !(med > 0.0f)) atomicOr(job.status, job.zero_bit);
-            st->nan_count = 0; st->alive = 0;
+            st->nan_count = 0; st->alive = 0; st->first_inv = 0;
             st->prefix[0] = st->prefix[1] = 0; st->rank[0] = st->rank[1] = 0;
         }
     }

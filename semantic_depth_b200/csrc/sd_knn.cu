@@ -360,7 +360,7 @@ template <int K> struct KnnCfg {
     static constexpr int list_cap = list_raw > 126 ? 126 : list_raw;      // phase-2 list entries per query (smem, 7-bit slots)
     // list entries are 16 bits: (row run of the query << 12) | offset inside that run (runs hold at most kExtreme = 4096
     // candidates); a small shared-memory footprint leaves the L1 to the sorted copies, which is what the sweeps wait on
-    static constexpr size_t smem_bytes = ((size_t)(list_cap + 1) * sizeof(uint16_t) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;   // + 1 spare row
+    static constexpr size_t smem_bytes = ((size_t)(list_cap + 2) * sizeof(uint16_t) + (size_t)kMaxRows * sizeof(int2)) * kKnnThreads;   // + 2 spare rows
 };
 
 template <int KS>
@@ -493,7 +493,9 @@ constexpr int kExtreme = 4096;                  // ... and beyond this it goes t
 #endif
 constexpr int kClaim = SD_KNN_CLAIM;
 #ifndef SD_KNN_WAVES
-#define SD_KNN_WAVES 16     // CTAs launched per SM (4 are resident; CTAs claim work until the queue is empty)
+#define SD_KNN_WAVES 5      // CTAs launched per SM = the resident set (CTAs claim work until the queue is empty).  Measured: 16 waves give
+                            // the same kernel time alone (1.02 vs 1.03 ms) but a slower pipelined step (2 825 vs 2 888 frames/s): surplus
+                            // CTAs keep every SM's slots taken until the queue is empty and delay the other batches' kernels
 #endif
 #ifndef SD_KNN_MINB
 #define SD_KNN_MINB 5       // resident CTAs per SM (96 registers; measured on B200: 4 -> 1.108 ms, 5 -> 1.063 ms, 6 spills -> 1.12 ms per 5-frame batch)
@@ -633,18 +635,22 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 }
                 if (todo) cnt = 0;
                 if (todo && !heavy) {
+                    // the list is filled through a saturating pointer: entry k goes to row min(k, kListCap + 1), so a pointer
+                    // that ends beyond row kListCap means "more than kListCap hits" (rows kListCap, kListCap + 1 are spare)
+                    uint16_t* lp = &s_list[0][tid];
+                    uint16_t* const lp_max = &s_list[kListCap + 1][tid];
                     for (int ri = 0; ri < nruns; ++ri) {
                         const int2 se = s_seg[ri][tid];
-                        // full batches need no bound checks; an overflowing list parks its writes in the spare row
+                        const int tag = (ri << 12) - se.x;                   // entry = (run << 12) | offset = tag + candidate index
                         int j0 = se.x;
-                        for (; j0 + kBatch <= se.y; j0 += kBatch) {
+                        for (; j0 + kBatch <= se.y; j0 += kBatch) {          // full batches need no bound checks
                             const float4* __restrict__ pc = J.sp + j0;
                             float4 c[kBatch];
 #pragma unroll
                             for (int u = 0; u < kBatch; ++u) c[u] = __ldg(pc + u);
 #pragma unroll
                             for (int u = 0; u < kBatch; ++u) {
-                                if (key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = (uint16_t)((ri << 12) | (j0 + u - se.x)); ++cnt; }
+                                if (key_of(c[u], qx, qy, qz) <= band) { *lp = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
                             }
                         }
                         if (j0 < se.y) {                                     // the tail as one masked batch: one round trip, not up to kBatch - 1
@@ -653,10 +659,11 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                             for (int u = 0; u < kBatch - 1; ++u) c[u] = __ldg(J.sp + min(j0 + u, se.y - 1));
 #pragma unroll
                             for (int u = 0; u < kBatch - 1; ++u) {
-                                if (j0 + u < se.y && key_of(c[u], qx, qy, qz) <= band) { s_list[min(cnt, kListCap)][tid] = (uint16_t)((ri << 12) | (j0 + u - se.x)); ++cnt; }
+                                if (j0 + u < se.y && key_of(c[u], qx, qy, qz) <= band) { *lp = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
                             }
                         }
                     }
+                    cnt = (int)(lp - &s_list[0][tid]) / kKnnThreads;         // min(hits, kListCap + 1)
                 }
                 // heavy lanes, one after the other, all 32 lanes on each
                 for (unsigned hm = __ballot_sync(SD_FULL, todo && heavy); hm; hm &= hm - 1) {

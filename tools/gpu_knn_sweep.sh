@@ -11,7 +11,7 @@ for spec in ${SWEEP}; do
       SD_KNN_CELL_SCALE=$cs timeout 600 python -m pytest tests/test_gpu_knn.py tests/test_gpu_fullsize.py -q -m gpu -x --timeout 600 > gpurun_out/sweep_test_${name}_$cs.log 2>&1
       echo "tests $name cs=$cs rc=$? $(tail -n 1 gpurun_out/sweep_test_${name}_$cs.log)"
     fi
-    SD_KNN_CELL_SCALE=$cs timeout 300 python bench.py --steps ${STEPS:-60} --warmup 6 --batches 3 --skip-cpu-baseline --skip-e2e --skip-configs > gpurun_out/sweep_${name}_$cs.json 2> gpurun_out/sweep_${name}_$cs.err
+    SD_KNN_CELL_SCALE=$cs timeout 300 python bench.py --steps ${STEPS:-60} --warmup 6 --batches 3 --skip-cpu-baseline --skip-e2e --skip-configs ${SWEEP_ARGS} > gpurun_out/sweep_${name}_$cs.json 2> gpurun_out/sweep_${name}_$cs.err
     python - <<PY
 import json
 try:

@@ -218,3 +218,25 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and 2 <= d["cpu_baseline"]["cores"] <= os.cpu_count()      # 2 processes x their k-d tree threads
     assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_host_placement_logic_on_cpu():
+    """semantic_depth_b200.hostmem: the pieces that do not need a GPU -- CPU-list parsing, the candidate rank -> GPU maps of
+    a job that is smaller than the box, placement calls degrading to no-ops where sysfs / the device is missing."""
+    import numpy as np
+    import torch
+    from semantic_depth_b200 import hostmem as h
+    assert h._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11] and h._parse_cpulist("") == []
+    assert h.candidate_device_maps(8, 8) == {"first": list(range(8))}
+    assert h.candidate_device_maps(4, 8) == {"first": [0, 1, 2, 3], "last": [4, 5, 6, 7], "spread": [0, 2, 4, 6]}
+    assert h.candidate_device_maps(2, 8)["spread"] == [0, 4] and h.candidate_device_maps(3, 4)["last"] == [1, 2, 3]
+    info = h.gpu_locality(0)                                  # no driver here: reported, not raised
+    assert info["numa_node"] == -1 and info["local_cpus"] == []
+    done = h.bind_to_gpu(0)
+    assert done["cpus"] is None and done["mempolicy"] is False
+    t = torch.zeros(1 << 20, dtype=torch.uint8)
+    hist = h.node_histogram(t.data_ptr(), t.numel())
+    assert sum(hist.values()) > 0 and all(isinstance(k, int) for k in hist)
+    # one rank, or as many ranks as GPUs: the plain map, nothing is measured
+    dev, rep = h.choose_device(0, 1)
+    assert dev == 0 and rep["map"] == "first"

@@ -637,8 +637,9 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                 if (todo && !heavy) {
                     // the list is filled through a saturating pointer: entry k goes to row min(k, kListCap + 1), so a pointer
                     // that ends beyond row kListCap means "more than kListCap hits" (rows kListCap, kListCap + 1 are spare)
-                    uint16_t* lp = &s_list[0][tid];
-                    uint16_t* const lp_max = &s_list[kListCap + 1][tid];
+                    uint16_t* const lbase = &s_list[0][tid];
+                    int lp = 0;                                              // element offset of the next entry
+                    constexpr int lp_max = (kListCap + 1) * kKnnThreads;
                     for (int ri = 0; ri < nruns; ++ri) {
                         const int2 se = s_seg[ri][tid];
                         const int tag = (ri << 12) - se.x;                   // entry = (run << 12) | offset = tag + candidate index
@@ -650,7 +651,7 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                             for (int u = 0; u < kBatch; ++u) c[u] = __ldg(pc + u);
 #pragma unroll
                             for (int u = 0; u < kBatch; ++u) {
-                                if (key_of(c[u], qx, qy, qz) <= band) { *lp = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
+                                if (key_of(c[u], qx, qy, qz) <= band) { lbase[lp] = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
                             }
                         }
                         if (j0 < se.y) {                                     // the tail as one masked batch: one round trip, not up to kBatch - 1
@@ -659,11 +660,11 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                             for (int u = 0; u < kBatch - 1; ++u) c[u] = __ldg(J.sp + min(j0 + u, se.y - 1));
 #pragma unroll
                             for (int u = 0; u < kBatch - 1; ++u) {
-                                if (j0 + u < se.y && key_of(c[u], qx, qy, qz) <= band) { *lp = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
+                                if (j0 + u < se.y && key_of(c[u], qx, qy, qz) <= band) { lbase[lp] = (uint16_t)(tag + j0 + u); lp = min(lp + kKnnThreads, lp_max); }
                             }
                         }
                     }
-                    cnt = (int)(lp - &s_list[0][tid]) / kKnnThreads;         // min(hits, kListCap + 1)
+                    cnt = lp / kKnnThreads;                                  // min(hits, kListCap + 1)
                 }
                 // heavy lanes, one after the other, all 32 lanes on each
                 for (unsigned hm = __ballot_sync(SD_FULL, todo && heavy); hm; hm &= hm - 1) {

@@ -364,7 +364,8 @@ int sd_ws_cloud(SdWorkspace* ws, int frame, int which, const float** d_x, const 
 int sd_ws_stage_src(SdWorkspace* ws, int frame, int stage, const int32_t** d_src);
 /* Stages whose filter is NOT materialised by a compaction (the MAD filters in front of a plane fit, when no RANSAC
  * hypotheses are given): the stage's cloud is the rows i < *d_rows of the chain's input with d_alive[i] != 0, in input
- * order; d_src[i] is the source pixel of row i.  stage = SD_CNT_ROAD_MAD_X, SD_CNT_FENCE_MAD_Y, SD_CNT_LEFT_MAD_X or SD_CNT_RIGHT_MAD_X;
+ * order; d_src[i] is the source pixel of row i.  stage = SD_CNT_FENCE_MAD_Y, SD_CNT_LEFT_MAD_X or SD_CNT_RIGHT_MAD_X (the road chain's
+ * input buffer is reused by its final compaction, so the road MAD stages are observable through their counts only);
  * SD_ERR_UNSUPPORTED when the stage is materialised (use sd_ws_stage_src) or not retained. */
 int sd_ws_stage_alive(SdWorkspace* ws, int frame, int stage, const int32_t** d_src, const uint8_t** d_alive, const int32_t** d_rows);
 

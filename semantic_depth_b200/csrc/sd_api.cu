@@ -1030,10 +1030,7 @@ extern "C" int sd_ws_stage_alive(SdWorkspace* ws, int frame, int stage, const in
     const size_t cap = (size_t)ws->cap;
     const FrameState* fs = ws->fs + frame;
     switch (stage) {
-        case SD_CNT_ROAD_MAD_X:          // after the plane-moment kernel the road bytes hold MAD y && MAD x
-            if (!pv->lazy_road) break;
-            *d_src = ws->road[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 0) * cap; *d_rows = &fs->n[SD_CNT_ROAD_Z];
-            return SD_OK;
+        // (the road chain's input buffer is reused by the final road compaction, so its MAD stages are not retained)
         case SD_CNT_FENCE_MAD_Y:         // survivors of remove_noise_by_mad inside the fused MAD y + |z| compaction
             *d_src = ws->fence[0].src + frame * cap; *d_alive = ws->cflags + ((size_t)frame * 4 + 3) * cap; *d_rows = &fs->n[SD_CNT_FENCE_GATHER];
             return SD_OK;

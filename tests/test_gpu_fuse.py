@@ -45,7 +45,7 @@ def check_against_oracle(res, f, o, eng=None):
             pts, src = eng.final_cloud(f, which)
             assert np.array_equal(src.cpu().numpy(), o["src"][stage]), f"final {which} cloud indices"
         # materialised stages (sd_ws_stage_src) and the filters the fused path keeps as alive bytes (sd_ws_stage_alive)
-        for stage in ("road_plane", "fence_abs_z", "fence_mad_y", "left_mad_x", "right_mad_x", "road_mad_x"):
+        for stage in ("road_plane", "fence_abs_z", "fence_mad_y", "left_mad_x", "right_mad_x"):
             src = eng.stage_src(f, stage, counts[stage])
             assert np.array_equal(src.cpu().numpy(), o["src"][stage]), stage
 

@@ -1236,7 +1236,11 @@ int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t 
     if (njobs <= 0) return SD_OK;
     // statistical filter applied to the sorted copies (if any) + per-cell statistics of what is left
     sor_mark_kernel<<<grid_for(3 * cap, kGridThreads, 4, njobs, 8), kGridThreads, 0, st>>>(d_jobs);
-    radius_kernel<<<grid_for(cap, kKnnThreads, 1, njobs, 16), kKnnThreads, 0, st>>>(d_jobs);
+#ifndef SD_RADIUS_WAVES
+#define SD_RADIUS_WAVES 5      // the resident set, like the k-NN kernel: surplus CTAs of a claim-until-empty kernel only hold slots
+                               // (measured: 16 -> 5 waves, pipelined step +1.8 %)
+#endif
+    radius_kernel<<<grid_for(cap, kKnnThreads, 1, njobs, SD_RADIUS_WAVES), kKnnThreads, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

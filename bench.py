@@ -326,7 +326,7 @@ def run_b200(a):
     input_bytes = nb * B * HW * 20
 
     # one CUDA graph per batch and slot; the only events inside the timed region bracket whole batches
-    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=False)
+    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph)
 
     # ---- expected answers (also builds job tables and captures the graphs): one pass over every
     #      (slot, batch) pair that the timed loop will use
@@ -622,7 +622,7 @@ def run_stream(a, rank, world, dev, dev_index, device_map, P, intr, barrier, max
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         for lg, dp in ex.map(gen, starts):
             d_logits.append(torch.from_numpy(lg).to(dev)); d_disp.append(torch.from_numpy(dp).to(dev))
-    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph, timing=False)
+    pipe = FramePipeline(H, W, B, slots=a.slots, device=dev, params=P, use_graphs=not a.no_graph)
     if d_logits:                                            # warm: job tables + one graph per slot and batch shape
         for _ in range(max(a.warmup, 1) * len(pipe.slots)):
             pipe.submit_device_stream(d_logits[0], d_disp[0], intr, tag=0)

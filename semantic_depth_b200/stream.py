@@ -76,7 +76,7 @@ class _Slot:
         self.engine = FusionEngine(height, width, max_frames=batch, max_hypotheses=max_hyp, device=device)
         self.stream = torch.cuda.Stream(device=device)
         self.done = torch.cuda.Event()
-        self.ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+        self.ev = {0: torch.cuda.Event(enable_timing=True), 4: torch.cuda.Event(enable_timing=True)}   # first / last kernel of a batch
         self.graphs = {}           # key -> CUDAGraph
         self.stage_logits = None   # device staging for host inputs
         self.stage_disp = None
@@ -96,16 +96,13 @@ class FramePipeline:
     """
 
     def __init__(self, height: int, width: int, batch: int, slots: int = 2, device="cuda:0",
-                 params: FusionParams | None = None, use_graphs: bool = True, timing: bool = False):
+                 params: FusionParams | None = None, use_graphs: bool = True):
         self.height, self.width, self.batch = height, width, batch
         self.device = torch.device(device)
         self.params = params or FusionParams()
         self.use_graphs = use_graphs
         self.slots = [_Slot(height, width, batch, self.device) for _ in range(slots)]
-        self.timing = timing
-        self.pixel_ms: list[float] = []     # pixel stage (3 kernels)
-        self.knn_ms: list[float] = []       # the k-NN kernel of the statistical filter
-        self.total_ms: list[float] = []     # first to last kernel of the batch
+        self.total_ms: list[float] = []     # first to last kernel of every retired batch (per-stage times: FusionEngine.stage_times)
         self._next = 0
 
     # -- internals ---------------------------------------------------------------------------------
@@ -113,10 +110,7 @@ class FramePipeline:
         if not slot.busy:
             return None
         slot.done.synchronize()
-        if self.timing:
-            self.pixel_ms.append(slot.ev[0].elapsed_time(slot.ev[1]))
-            self.knn_ms.append(slot.ev[2].elapsed_time(slot.ev[3]))
-        if self.timing or slot.timed_total:
+        if slot.timed_total:
             self.total_ms.append(slot.ev[0].elapsed_time(slot.ev[4]))
         raw = np.frombuffer(slot.host_results[: slot.nbytes].numpy().tobytes(), dtype=RESULT_DTYPE).copy()
         slot.busy = False
@@ -132,38 +126,22 @@ class FramePipeline:
         return g
 
     def _launch(self, slot: _Slot, logits: torch.Tensor, disp: torch.Tensor, intr: Intrinsics, key):
-        """Enqueue one batch on the slot's stream.  With timing on, the path is split into four graphs (or four
-        eager calls) -- pixel stage | cloud stages up to the search grid | k-NN kernel | the rest -- so that
-        torch events can bracket the pixel stage and the k-NN kernel."""
+        """Enqueue one batch on the slot's stream: one CUDA graph per key (captured after one eager call that builds the job
+        tables), bracketed by two events."""
         eng = slot.engine
         b = logits.shape[0]
+        slot.ev[0].record(slot.stream)
         if self.use_graphs:
             g = slot.graphs.get(key)
             if g is None:
                 eng.enqueue(logits, disp, intr, self.params)          # eager once: builds the job tables
                 slot.stream.synchronize()
-                g = (tuple(self._capture(slot, logits, disp, intr, m) for m in (1, 2, 4, 8))
-                     if self.timing else (self._capture(slot, logits, disp, intr, 15),))
+                g = self._capture(slot, logits, disp, intr, 15)
                 slot.graphs[key] = g
-            if self.timing:
-                for k, gk in enumerate(g):
-                    slot.ev[k].record(slot.stream)
-                    gk.replay()
-                slot.ev[4].record(slot.stream)
-            else:
-                slot.ev[0].record(slot.stream)
-                g[0].replay()
-                slot.ev[4].record(slot.stream)
-        elif self.timing:
-            for k, m in enumerate((1, 2, 4, 8)):
-                slot.ev[k].record(slot.stream)
-                eng.set_stage_mask(m); eng.enqueue(logits, disp, intr, self.params)
-            eng.set_stage_mask(15)
-            slot.ev[4].record(slot.stream)
+            g.replay()
         else:
-            slot.ev[0].record(slot.stream)
             eng.enqueue(logits, disp, intr, self.params)
-            slot.ev[4].record(slot.stream)
+        slot.ev[4].record(slot.stream)
         slot.nbytes = b * C.sizeof(SdFrameResult)
         slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
         slot.done.record(slot.stream)
@@ -277,9 +255,6 @@ class FramePipeline:
                 eng.enqueue_scores(*args)
             slot.nbytes = b * C.sizeof(SdFrameResult)
             slot.host_results[: slot.nbytes].copy_(eng._results[: slot.nbytes], non_blocking=True)
-            if self.timing:                                   # keep the event bookkeeping of _retire valid
-                for e in slot.ev:
-                    e.record(slot.stream)
             slot.done.record(slot.stream)
             slot.busy = True
             slot.timed_total = False

@@ -206,6 +206,24 @@ int sd_ply_rows_f64(const double* d_x, const double* d_y, const double* d_z, con
 int sd_overlay_masks(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int height, int width,
                      const int32_t* road_rgba, const int32_t* fence_rgba, uint8_t* d_out, int32_t* d_scratch, void* stream);
 
+/* SURVEY.md 8f rank 4 (banner + putText): the result banner process_frame draws on the segmented frame
+ * (semantic_depth.py:339-394: cv2.rectangle(frame, (0,0), (w, int(0.2*h)), (156,157,159), -1) and up to seven
+ * cv2.putText(..., fontFace=16, fontScale 2 / 4, thickness 2 / 5) lines; live twin
+ * semantic_depth_cityscapes_sequence.py:304-327 with font scales 2 and 2.2), in place on d_frames [B][H][W][3] uint8.
+ *   d_rects  [n_rects][6]  int32 {frame, x0, y0, x1, y1, colour}: filled, corners inclusive and ordered, clipped to the frame
+ *   d_places [n_places][5] int32 {frame, bitmap, x, y, colour}: bitmap `bitmap` of the atlas pasted with its cell's
+ *            top-left pixel at (x, y), clipped to the frame
+ *   d_glyph_bits [n_bitmaps][cell_height][cell_words] uint32: bit b of word k of a row = pixel 32*k + b of that row
+ *   colour = channel0 | channel1 << 8 | channel2 << 16 (the frame's own channel order, like cv2's Scalar).
+ * The atlas (semantic_depth_b200/data/hershey_atlas.npz) is baked from OpenCV's own Hershey rasteriser for the reference's
+ * (fontFace, fontScale, thickness) presets; the pen arithmetic that picks bitmap and position (16.16 fixed point, cvRound)
+ * is host glue (semantic_depth_b200/frame_ops.py).  Rectangles are drawn before glyphs; glyphs of one call may overlap
+ * only if they share a colour (one call per run of equally coloured putText lines keeps cv2's drawing order).
+ * Never synchronises. */
+int sd_draw_banner(uint8_t* d_frames, int batch, int height, int width, const int32_t* d_rects, int n_rects,
+                   const uint32_t* d_glyph_bits, int n_bitmaps, int cell_height, int cell_words,
+                   const int32_t* d_places, int n_places, void* stream);
+
 /* ---- per-call cloud ops (the pcl.py call surface; n is known to the host) -------------------- */
 /* np.median of a column (pcl.py:78,80): h_out[0] = median(col), h_out[1] = median(|col - median|). */
 int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream);

@@ -90,6 +90,7 @@ SIGNATURES = {
     "sd_ply_rows_f64": (_I, [_P, _P, _P, _P, _I, _P, C.c_ulonglong, C.POINTER(C.c_ulonglong), _P, _P]),
     "sd_resize_cubic_u8": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "sd_overlay_masks": (_I, [_P, _P, _I, _I, _I, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P, _P]),
+    "sd_draw_banner": (_I, [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _P, _I, _P]),
     "sd_median_mad": (_I, [_P, _I, C.POINTER(C.c_float), _P, _P]),
     "sd_filter": (_I, [_P, _P, _P, _P, _I, C.POINTER(SdPredicate), _P, _P, _P, _P, C.POINTER(C.c_int32), _P, _P]),
     "sd_plane_fit": (_I, [_P, _P, _P, _I, _I, C.POINTER(C.c_double), C.POINTER(C.c_int32), _P, _P]),

@@ -472,6 +472,20 @@ extern "C" int sd_overlay_masks(const uint8_t* d_frame, const uint8_t* d_labels,
     return sd_launch_overlay(d_frame, d_labels, batch, height * width, L, d_scratch, d_out, (cudaStream_t)stream);
 }
 
+extern "C" int sd_draw_banner(uint8_t* d_frames, int batch, int height, int width, const int32_t* d_rects, int n_rects,
+                              const uint32_t* d_glyph_bits, int n_bitmaps, int cell_height, int cell_words,
+                              const int32_t* d_places, int n_places, void* stream) {
+    if (!d_frames || batch < 1 || height < 1 || width < 1 || n_rects < 0 || n_places < 0)
+        return fail(SD_ERR_INVALID, "sd_draw_banner: bad argument");
+    if ((long long)height * width > 0x7fffffffll / 4) return fail(SD_ERR_INVALID, "sd_draw_banner: frame too large");
+    if (n_rects > 65535) return fail(SD_ERR_INVALID, "sd_draw_banner: at most 65535 rectangles per call");
+    if (n_rects > 0 && !d_rects) return fail(SD_ERR_INVALID, "sd_draw_banner: null rectangles");
+    if (n_places > 0 && (!d_places || !d_glyph_bits || n_bitmaps < 1 || cell_height < 1 || cell_words < 1))
+        return fail(SD_ERR_INVALID, "sd_draw_banner: glyph placements need an atlas");
+    return sd_launch_banner(d_frames, batch, height, width, d_rects, n_rects, d_glyph_bits, n_bitmaps, cell_height, cell_words,
+                            d_places, n_places, (cudaStream_t)stream);
+}
+
 extern "C" int sd_median_mad(const float* d_col, int n, float* h_out, SdWorkspace* ws, void* stream) {
     int rc = check_n(ws, n); if (rc) return rc;
     if (!d_col || !h_out) return fail(SD_ERR_INVALID, "sd_median_mad: null argument");

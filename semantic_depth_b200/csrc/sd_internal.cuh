@@ -310,6 +310,9 @@ int sd_launch_resize_cubic_u8(const uint8_t* d_src, int batch, int src_h, int sr
                               cudaStream_t st);
 int sd_launch_overlay(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int hw, const sd::OverlayLayers& layers,
                       int* d_counts, uint8_t* d_out, cudaStream_t st);
+int sd_launch_banner(uint8_t* d_frames, int batch, int h, int w, const int32_t* d_rects, int nrects,
+                     const uint32_t* d_bits, int nbitmaps, int cell_h, int words, const int32_t* d_places, int nplaces,
+                     cudaStream_t st);
 int sd_launch_ransac(const sd::RansacJob* d_jobs, int njobs, int cap, int n_hyp, cudaStream_t st);
 int sd_launch_finalize(const sd::FinalJob* d_jobs, int njobs, const SdParams* params, cudaStream_t st);
 int sd_launch_pixel(const float* d_logits, const float* d_disp, const double* d_lmask, const double* d_rmask,

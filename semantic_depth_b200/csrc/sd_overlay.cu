@@ -105,6 +105,57 @@ overlay_blend_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Result banner of process_frame (semantic_depth.py:339-394, sequence:304-327): cv2.rectangle(..., -1) + cv2.putText.
+// The glyph bitmaps come from an atlas baked from OpenCV's own Hershey rasteriser (semantic_depth_b200/data/
+// make_hershey_atlas.py); the host decides which bitmap goes where (pen arithmetic in 16.16 fixed point, frame_ops.py).
+//   rect  = {frame, x0, y0, x1, y1, colour}: inclusive corners, already ordered; clipped here
+//   place = {frame, bitmap, x, y, colour}  : top-left pixel of the bitmap's cell; clipped here
+// colour = channel 0 | channel 1 << 8 | channel 2 << 16, in the frame's own channel order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kOverlayThreads)
+banner_rect_kernel(uint8_t* __restrict__ frames, int batch, int h, int w, const int32_t* __restrict__ rects) {
+    const int32_t* r = rects + 6 * blockIdx.y;
+    const int f = r[0];
+    const int x0 = max(r[1], 0), y0 = max(r[2], 0), x1 = min(r[3], w - 1), y1 = min(r[4], h - 1);
+    if (f < 0 || f >= batch || x1 < x0 || y1 < y0) return;
+    const uint32_t col = (uint32_t)r[5];
+    const int rowbytes = (x1 - x0 + 1) * 3;
+    const long long total = (long long)rowbytes * (y1 - y0 + 1);
+    uint8_t* base = frames + ((size_t)f * h * w) * 3;
+    for (long long i = (long long)blockIdx.x * kOverlayThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kOverlayThreads) {
+        const int row = (int)(i / rowbytes), b = (int)(i - (long long)row * rowbytes);
+        base[((size_t)(y0 + row) * w + x0) * 3 + b] = (uint8_t)(col >> (8 * (b % 3)));
+    }
+}
+
+constexpr int kGlyphThreads = 128;
+__global__ void __launch_bounds__(kGlyphThreads)
+banner_glyph_kernel(uint8_t* __restrict__ frames, int batch, int h, int w, const uint32_t* __restrict__ bits, int nbitmaps,
+                    int cell_h, int words, const int32_t* __restrict__ places) {
+    const int32_t* p = places + 5 * blockIdx.x;
+    const int f = p[0], g = p[1], px = p[2], py = p[3];
+    if (f < 0 || f >= batch || g < 0 || g >= nbitmaps) return;
+    const uint32_t col = (uint32_t)p[4];
+    const uint32_t* bm = bits + (size_t)g * cell_h * words;
+    uint8_t* base = frames + ((size_t)f * h * w) * 3;
+    for (int i = threadIdx.x; i < cell_h * words; i += kGlyphThreads) {
+        uint32_t v = __ldg(bm + i);
+        if (!v) continue;
+        const int row = i / words, wd = i - row * words;
+        const int y = py + row;
+        if (y < 0 || y >= h) continue;
+        while (v) {
+            const int b = __ffs(v) - 1;
+            v &= v - 1;
+            const int x = px + wd * 32 + b;
+            if (x < 0 || x >= w) continue;
+            uint8_t* q = base + ((size_t)y * w + x) * 3;
+            q[0] = (uint8_t)col; q[1] = (uint8_t)(col >> 8); q[2] = (uint8_t)(col >> 16);
+        }
+    }
+}
+
 }  // namespace sd
 
 int sd_launch_overlay(const uint8_t* d_frame, const uint8_t* d_labels, int batch, int hw, const sd::OverlayLayers& layers,
@@ -118,6 +169,21 @@ int sd_launch_overlay(const uint8_t* d_frame, const uint8_t* d_labels, int batch
                                         reinterpret_cast<uintptr_t>(d_out)) & 3) == 0;
     if (vec) overlay_blend_kernel<true><<<dim3(per, batch), kOverlayThreads, 0, st>>>(d_frame, d_labels, hw, layers, d_counts, d_out);
     else overlay_blend_kernel<false><<<dim3(per, batch), kOverlayThreads, 0, st>>>(d_frame, d_labels, hw, layers, d_counts, d_out);
+    SD_LAUNCH_CHECK();
+    return SD_OK;
+}
+
+int sd_launch_banner(uint8_t* d_frames, int batch, int h, int w, const int32_t* d_rects, int nrects,
+                     const uint32_t* d_bits, int nbitmaps, int cell_h, int words, const int32_t* d_places, int nplaces,
+                     cudaStream_t st) {
+    using namespace sd;
+    if (nrects > 0) {
+        // rectangles first (the text is drawn over the banner); a rectangle is at most the whole frame
+        const int per = max(1, min(ceil_div(h * w * 3, kOverlayThreads * 16), (148 * 8) / nrects + 1));
+        banner_rect_kernel<<<dim3(per, nrects), kOverlayThreads, 0, st>>>(d_frames, batch, h, w, d_rects);
+    }
+    if (nplaces > 0)
+        banner_glyph_kernel<<<nplaces, kGlyphThreads, 0, st>>>(d_frames, batch, h, w, d_bits, nbitmaps, cell_h, words, d_places);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

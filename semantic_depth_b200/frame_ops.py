@@ -132,6 +132,44 @@ def segment_frame(frame, logits, prob_thr: float = 0.5):
     return _back((lab & 1) != 0, was_torch), _back((lab & 2) != 0, was_torch), _back(out, was_torch)
 
 
+def draw_banner(frames, rects=(), texts=()):
+    """``cv2.rectangle(img, pt1, pt2, color, -1)`` / ``cv2.putText(img, text, org, 16, font_scale, color, thickness)`` on the
+    GPU for the reference's font presets; see ``semantic_depth_b200.banner.draw_banner``.  Returns the frames."""
+    from . import banner
+    return banner.draw_banner(frames, rects, texts)[0]
+
+
+def result_banner(segmented_frame, depth, left_pt_rw, right_pt_rw, dist_rw, left_pt_f2f=None, right_pt_f2f=None, dist_f2f=None,
+                  is_city=True, approach="both", original_size=None):
+    """Section 9 of ``process_frame`` (semantic_depth.py:339-394): the segmented frame up-sampled to the original size with
+    ``cv2.resize(..., INTER_CUBIC)`` (when ``original_size`` = (width, height) is given), the grey banner over its top 20 % and
+    the result lines.  NumPy in -> NumPy out, CUDA tensor in -> CUDA tensor out."""
+    from . import banner
+    was_torch = isinstance(segmented_frame, torch.Tensor)
+    t = segmented_frame if was_torch else torch.from_numpy(np.ascontiguousarray(segmented_frame))
+    t = t.to("cuda")
+    t = resize_cubic(t, original_size) if original_size is not None else t.clone()
+    h, w = int(t.shape[0]), int(t.shape[1])
+    rects, texts = banner.result_banner_spec(h, w, depth, left_pt_rw, right_pt_rw, dist_rw, left_pt_f2f, right_pt_f2f, dist_f2f,
+                                             is_city=is_city, approach=approach)
+    out, _ = banner.draw_banner(t.contiguous(), rects, texts)
+    return _back(out, was_torch)
+
+
+def sequence_banner(segmented_frame, depth, line_found, left_pt_rw=None, right_pt_rw=None, dist_rw=None, original_size=None):
+    """Section 9 of the sequence driver (semantic_depth_cityscapes_sequence.py:304-327): up-sampling, banner over the top 25 %
+    and three result lines, or the green "Cannot compute ..." line when no road point fell into the slab."""
+    from . import banner
+    was_torch = isinstance(segmented_frame, torch.Tensor)
+    t = segmented_frame if was_torch else torch.from_numpy(np.ascontiguousarray(segmented_frame))
+    t = t.to("cuda")
+    t = resize_cubic(t, original_size) if original_size is not None else t.clone()
+    h, w = int(t.shape[0]), int(t.shape[1])
+    rects, texts = banner.sequence_banner_spec(h, w, depth, bool(line_found), left_pt_rw, right_pt_rw, dist_rw)
+    out, _ = banner.draw_banner(t.contiguous(), rects, texts)
+    return _back(out, was_torch)
+
+
 def upsample_scores(scores, weights, bias):
     """FCN-8s' last layer, ``conv2d_transpose(second_skip, 3, 16x16, stride 8, 'same')`` (fcn8s/fcn.py:207-213):
     scores [h,w,3] -> logits [8h*8w, 3] fp32, evaluated by the label kernel (fp32, fixed summation order)."""

@@ -21,7 +21,9 @@ networks runs on the GPU in one fused call:
     cv2.resize of the segmented frame back             :sequence 304   resize_cubic_u8 kernel
     PointCloud2Ply(road3D, road_colors) + rw line      :sequence 372-376   ply kernels
 
-The text banner (cv2.rectangle / putText, sequence:309-332) and cv2.imwrite stay with the caller.
+    cv2.rectangle / cv2.putText of the banner         :339-394, sequence 306-327   banner kernels (``banner=...``)
+
+cv2.imwrite stays with the caller.
 """
 from __future__ import annotations
 
@@ -63,7 +65,7 @@ class FrameProcessor:
 
     def __init__(self, frame_segmenter, frame_depther, input_shape, approach="both", depth=10.0, verbose=False,
                  intrinsics: Intrinsics | None = None, disp_multiplier: float | None = None,
-                 params: FusionParams | None = None):
+                 params: FusionParams | None = None, banner: str | None = None, is_city: bool = True):
         if approach not in ("rw", "both"):
             raise ValueError("approach must be 'rw' or 'both'")
         for obj, name in ((frame_segmenter, "logits"), (frame_depther, "disparities")):
@@ -79,6 +81,10 @@ class FrameProcessor:
         if disp_multiplier is not None:
             self.disp_multiplier = float(disp_multiplier)
         self.params = (params or FusionParams()).replace(depth=self.depth, approach=approach)
+        if banner not in (None, "single", "sequence"):
+            raise ValueError("banner must be None, 'single' (semantic_depth.py:339-394) or 'sequence' (sequence:304-327)")
+        self.banner = banner
+        self.is_city = bool(is_city)
 
     def _intrinsics(self, original_width: int) -> Intrinsics:
         mult = float(original_width) if self.disp_multiplier is None else float(self.disp_multiplier)
@@ -124,6 +130,11 @@ class FrameProcessor:
             left_f2f, right_f2f = res.raw["left_pt"][0][None, :].copy(), res.raw["right_pt"][0][None, :].copy()
 
         segmented = frame_ops.resize_cubic(overlaid, (w0, h0))                                # sequence:304
+        if self.banner == "sequence":                                                         # sequence:306-327
+            segmented = frame_ops.sequence_banner(segmented, self.depth, line_found, left_rw, right_rw, dist_rw)
+        elif self.banner == "single" and line_found and (self.approach == "rw" or dist_f2f is not None):   # :346-394
+            segmented = frame_ops.result_banner(segmented, self.depth, left_rw, right_rw, dist_rw, left_f2f, right_f2f, dist_f2f,
+                                                is_city=self.is_city, approach=self.approach)
         out = FrameOutput(dist_rw, dist_f2f, line_found, left_rw, right_rw, left_f2f, right_f2f,
                           road_mask[..., 0].cpu().numpy(), fence_mask[..., 0].cpu().numpy(), segmented.cpu().numpy(),
                           road3D, road_colors, status, status_to_names(status), res.counts(0))

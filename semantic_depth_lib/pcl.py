@@ -12,6 +12,8 @@ and the reference lines each function follows.  Additive entry points cover what
 * ``fuse_frames``             -- the whole fusion section of process_frame, :183-324, batched
 * ``resize_cubic``            -- cv2.resize(..., INTER_CUBIC) of the input frame, semantic_depth.py:110-112
 * ``overlay_masks`` / ``segment_frame`` -- the masks and the overlaid frame of SegmentFrame.segment_frame, :547-570
+* ``draw_banner`` / ``result_banner`` / ``sequence_banner`` -- cv2.rectangle + cv2.putText of the result banner,
+  semantic_depth.py:339-394 and semantic_depth_cityscapes_sequence.py:304-327
 * ``upsample_scores`` / ``fuse_frames_from_scores`` -- the same path fed by FCN-8s' unexpanded head
   (``second_skip`` + the last transposed convolution, fcn8s/fcn.py:207-213)
 """
@@ -23,5 +25,5 @@ from semantic_depth_b200.pcl_gpu import (  # noqa: F401
 )
 from semantic_depth_b200.frame_ops import (  # noqa: F401
     labels_from_logits, post_process_disparity, reproject_to_3d, fuse_frames, upsample_scores, fuse_frames_from_scores, resize_cubic,
-    overlay_masks, segment_frame,
+    overlay_masks, segment_frame, draw_banner, result_banner, sequence_banner,
 )

@@ -79,3 +79,29 @@ def test_process_frame_rejects_bad_producers(cuda_device):
         FrameProcessor(object(), _Depther(None), (H, W))
     with pytest.raises(ValueError):
         FrameProcessor(_Segmenter(None), _Depther(None), (H, W), approach="f2f")
+
+
+@pytest.mark.parametrize("mode", ["single", "sequence"])
+def test_process_frame_draws_the_banner(cuda_device, mode):
+    """Section 9 of process_frame (semantic_depth.py:339-394 / sequence:304-327) on a Cityscapes-sized original."""
+    from oracle import banner_ref
+    from semantic_depth_b200 import banner
+    logits, disp, _ = make_frame(H, W, seed=4)
+    rng = np.random.default_rng(11)
+    h0, w0 = 1024, 2048
+    original = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+    intr = Intrinsics.synthetic(W)
+    plain = FrameProcessor(_Segmenter(logits), _Depther(disp), (H, W), approach="both", depth=10.0, intrinsics=intr,
+                           disp_multiplier=W).process_frame(original)
+    out = FrameProcessor(_Segmenter(logits), _Depther(disp), (H, W), approach="both", depth=10.0, intrinsics=intr,
+                         disp_multiplier=W, banner=mode).process_frame(original)
+    assert out.line_found and out.dist_rw == plain.dist_rw
+    if mode == "single":
+        rects, texts = banner.result_banner_spec(h0, w0, 10.0, out.left_pt_rw, out.right_pt_rw, out.dist_rw,
+                                                 out.left_pt_f2f, out.right_pt_f2f, out.dist_f2f, is_city=True, approach="both")
+    else:
+        rects, texts = banner.sequence_banner_spec(h0, w0, 10.0, True, out.left_pt_rw, out.right_pt_rw, out.dist_rw)
+    want = banner_ref.draw(plain.segmented_frame, [(p1, p2, c) for _, p1, p2, c in rects],
+                           [(t, org, s, th, c) for _, t, org, s, th, c in texts])
+    assert np.array_equal(out.segmented_frame, want)
+    assert not np.array_equal(out.segmented_frame, plain.segmented_frame)

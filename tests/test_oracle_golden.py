@@ -187,6 +187,37 @@ def test_overlay_oracle_against_pil_golden(golden_dir):
     assert not overlay_ref.mask_rgba(np.array([[False, False]]), overlay_ref.ROAD_RGBA).any()
 
 
+def test_banner_oracle_against_cv2_golden(golden_dir):
+    """SURVEY 8f rank 4 (banner + putText): oracle.banner_ref + the baked glyph atlas + the product's own line / position glue
+    against frames the reference's own statements drew with cv2 (make_golden_banner.py)."""
+    from oracle import banner_ref
+    from semantic_depth_b200 import banner
+    from tests_banner_cases import CASES, VALUES, base_frame
+    z = np.load(os.path.join(golden_dir, "banner_vectors.npz"))
+    assert [str(n) for n in z["names"]] == [c[0] for c in CASES]
+    for i, (name, driver, h, w, kw) in enumerate(CASES):
+        if driver == "single":
+            rects, texts = banner.result_banner_spec(h, w, kw["depth"], VALUES["left_pt_rw"], VALUES["right_pt_rw"], VALUES["dist_rw"],
+                                                     VALUES["left_pt_f2f"], VALUES["right_pt_f2f"], VALUES["dist_f2f"],
+                                                     is_city=kw["is_city"], approach=kw["approach"])
+        else:
+            rects, texts = banner.sequence_banner_spec(h, w, kw["depth"], kw["line_found"], VALUES["left_pt_rw"],
+                                                       VALUES["right_pt_rw"], VALUES["dist_rw"])
+        rows = int(z[f"case{i}_shape"][2])
+        base = base_frame(h, w, i)
+        got = banner_ref.draw(base, [(p1, p2, c) for _, p1, p2, c in rects], [(t, org, s, th, c) for _, t, org, s, th, c in texts])
+        assert np.array_equal(got[:rows], z[f"case{i}_top"]), name
+        assert np.array_equal(got[rows:], base[rows:]), name
+        # the product's placement arithmetic is the oracle's (same pen pixel, same bitmap) for every line
+        for _, text, org, scale, thick, _ in texts:
+            pi = banner.preset_index(scale, thick)
+            assert pi == banner_ref.preset_of(scale, thick)
+            assert len(banner.layout_text(pi, text, org)) == len(text)
+    assert banner.layout_text(0, "\u00e9", (0, 50)) == banner.layout_text(0, "?", (0, 50))      # cv2 draws '?' for non-ASCII
+    with pytest.raises(ValueError):
+        banner.preset_index(3.0, 2)
+
+
 def test_config4_fixture_reproducible(golden_dir):
     """BASELINE.json configs[3]: the committed answers of the 2 M-point statistical filter are what the oracle computes."""
     import hashlib
@@ -201,7 +232,9 @@ def test_config4_fixture_reproducible(golden_dir):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/semantic_depth_lib"), reason="reference tree not present (GPU box)")
 @pytest.mark.parametrize("script,args", [("make_golden.py", ["--verify"]), ("make_golden_ply.py", ["--verify"]),
-                                         ("make_golden_overlay.py", ["--verify"]), ("make_golden_resize.py", ["--verify"])])
+                                         ("make_golden_overlay.py", ["--verify"]), ("make_golden_resize.py", ["--verify"]),
+                                         ("make_golden_banner.py", ["--verify"]),
+                                         ("../../semantic_depth_b200/data/make_hershey_atlas.py", ["--verify"])])
 def test_committed_fixtures_equal_live_reference(golden_dir, script, args):
     """Build container only: re-run the generators against the reference's own code (its unmodified pcl.py, the
     DepthFrame methods lifted from semantic_depth.py, its PointCloud2Ply; PIL's paste for the overlay) and compare with the

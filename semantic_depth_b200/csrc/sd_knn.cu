@@ -493,12 +493,20 @@ constexpr int kExtreme = 4096;                  // ... and beyond this it goes t
 #endif
 constexpr int kClaim = SD_KNN_CLAIM;
 #ifndef SD_KNN_WAVES
-#define SD_KNN_WAVES 5      // CTAs launched per SM = the resident set (CTAs claim work until the queue is empty).  Measured: 16 waves give
+#define SD_KNN_WAVES 7      // CTAs launched per SM = the resident set (CTAs claim work until the queue is empty).  Measured: 16 waves give
                             // the same kernel time alone (1.02 vs 1.03 ms) but a slower pipelined step (2 825 vs 2 888 frames/s): surplus
                             // CTAs keep every SM's slots taken until the queue is empty and delay the other batches' kernels
 #endif
+#ifndef SD_KNN_GRID_SMEM
+#define SD_KNN_GRID_SMEM 1  // the CTA-uniform grid geometry lives in shared memory (an LDS at each use) instead of ~20 registers per thread:
+                            // 80 / 72 registers without / with 24 bytes of spill instead of 96, i.e. 6 / 7 resident CTAs per SM instead of 5
+#endif
 #ifndef SD_KNN_MINB
-#define SD_KNN_MINB 5       // resident CTAs per SM (96 registers; measured on B200: 4 -> 1.108 ms, 5 -> 1.063 ms, 6 spills -> 1.12 ms per 5-frame batch)
+#define SD_KNN_MINB 7       // resident CTAs per SM.  The search kernels are bound by dependent-load latency at low occupancy, so warps in
+                            // flight are what pays.  Measured on B200 (5-frame batch, kernel alone / pipelined step): geometry in registers,
+                            // 5 CTAs at 96 registers 1.01-1.03 ms / 2 944-2 953 frames/s (6 CTAs spill: 1.12 ms); geometry in shared memory,
+                            // 5 CTAs 0.975 ms / 2 991, 6 CTAs 0.990 / 3 032, 7 CTAs 0.976-0.98 / 3 070, 8 CTAs (64 registers, 77 KB of L1 left)
+                            // 1.009 / 2 934
 #endif
 template <int KS>
 __global__ void __launch_bounds__(kKnnThreads, (KS <= 11 ? SD_KNN_MINB : 1))
@@ -511,8 +519,24 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
     int2 (*s_seg)[kKnnThreads] = reinterpret_cast<int2 (*)[kKnnThreads]>(s_dyn);                   // (start, end) of a row run
     uint16_t (*s_list)[kKnnThreads] = reinterpret_cast<uint16_t (*)[kKnnThreads]>(s_dyn + kMaxRows * kKnnThreads);   // candidates: (run << 12) | offset
     auto listed = [&](int e, int t) -> int { const unsigned v = s_list[e][t]; return s_seg[v >> 12][t].x + (int)(v & 4095u); };
+#if SD_KNN_GRID_SMEM >= 2
+    __shared__ KnnJob s_job;
+    if (threadIdx.x == 0) s_job = jobs[blockIdx.y];
+    __syncthreads();
+    const KnnJob& J = s_job;
+#else
     const KnnJob J = jobs[blockIdx.y];
+#endif
+#if SD_KNN_GRID_SMEM
+    // the grid geometry is CTA-uniform: kept in shared memory it costs an LDS where it is used instead of ~20 registers
+    // per thread for the whole kernel
+    __shared__ GridRt s_grid;
+    if (threadIdx.x == 0) s_grid = load_grid(J.gs);
+    __syncthreads();
+    const GridRt& g = s_grid;
+#else
     const GridRt g = load_grid(J.gs);
+#endif
     const int keff = min(J.k, g.n);
     const int need = min(Cfg::min_fed, g.n);
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
@@ -1015,59 +1039,100 @@ sor_mark_kernel(const KnnJob* __restrict__ jobs) {
 // Level: the finest one whose 3x3 cells around the query hold more than `cap` points (dense regions: the
 // walk stops after ~cap tests right around the query); sparse regions count at the coarsest level whose cells
 // are at most a quarter of the radius.
-__global__ void __launch_bounds__(kKnnThreads)
+#ifndef SD_RADIUS_GATHER
+#define SD_RADIUS_GATHER 1   // 1: queries that need the candidate walk are gathered into full warps (0: every lane walks its own query)
+#endif
+// Most queries of a road cloud are decided by the whole-cell shortcut (their ball holds a few dense level-1 cells), the
+// rest walk candidates.  Lane by lane that left the walk loop -- 60 % of the kernel's instructions -- running with 5.6 of
+// 32 lanes.  So a warp works in two phases: it claims chunks of 32 queries and runs the shortcut on them, pushing the
+// queries that still need a walk into a small per-warp queue (claim order is kept: neighbours stay neighbours), and as soon
+// as 32 of them wait -- or the job's queries are used up -- it walks 32 at a time, one per lane.
+#ifndef SD_RADIUS_MINB
+#define SD_RADIUS_MINB 8     // resident CTAs per SM (64 registers, 38 bytes of spill; the kernel needs next to no shared memory).  Measured with
+                             // the k-NN kernel at 7 CTAs: 5 -> 3 070, 6 -> 3 010, 8 -> 3 107, 10 -> 3 087 frames/s
+#endif
+__global__ void __launch_bounds__(kKnnThreads, SD_RADIUS_MINB)
 radius_kernel(const KnnJob* __restrict__ jobs) {
+    __shared__ int s_wq[kKnnThreads / 32][64];
     const KnnJob J = jobs[blockIdx.y];
+#if SD_KNN_GRID_SMEM
+    __shared__ GridRt s_grid;                                    // CTA-uniform geometry: an LDS where it is used instead of ~20 registers
+    if (threadIdx.x == 0) s_grid = load_grid(J.gs);
+    __syncthreads();
+    const GridRt& g = s_grid;
+#else
     const GridRt g = load_grid(J.gs);
+#endif
     const double r = J.radius, r2 = r * r;
     const float r2_in = __double2float_rd(r2 * (1.0 - 3e-6)), r2_out = __double2float_ru(r2 * (1.0 + 3e-6));
     const int cap = J.count_cap;
     const float finf = __int_as_float(0x7f800000);
     const float r2_sure = __double2float_rd(r2 * (1.0 - 1e-4));
     const int ga2 = J.gs->a2;
+    const int lane = lane_id();
+    int* const wq = s_wq[warp_id()];
     int Lmax = 0;
 #pragma unroll
     for (int l = 1; l < kLevels; ++l) if (g.cell * (double)(1 << (2 * l)) <= 0.25 * r) Lmax = l;   // measured: ~8 rows of small cells beat 3 rows of big ones
+    int qhead = 0, qcount = 0;                                   // ring of waiting walkers (warp-uniform)
+    bool exhausted = false;
     while (true) {
-      int cbase = 0;
-      if (lane_id() == 0) cbase = atomicAdd(&J.gs->work, 32 * kClaim);
-      cbase = __shfl_sync(SD_FULL, cbase, 0);
-      if (cbase >= g.n) break;
-      for (int sub = 0; sub < kClaim; ++sub) {
-        const int wbase = cbase + 32 * sub;
-        if (wbase >= g.n) break;
-        const int i = wbase + lane_id();
-        if (i >= g.n) continue;
-        const float4 qp = __ldg(J.sp + i);
-        const float qx = qp.x, qy = qp.y, qz = qp.z;
-        if (qx == finf) continue;                               // removed by the statistical filter (count already 0)
-        const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
-        const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
-        if (cap >= 0) {
-            // whole level-1 cells inside the ball: their alive points count without being looked at
-            const float cell1 = (float)(g.cell * 4.0), qa = pick_axis(ga2, qx, qy, qz);
-            const float f0 = (float)(q0 - g.o0), f1 = (float)(q1 - g.o1);        // query relative to the grid origin
-            const int k0 = c0 >> 2, k1 = c1 >> 2;
-            int sure = 0;
+      // ---- phase A: claim chunks and decide what the shortcut can decide
+      while (!exhausted && qcount < (SD_RADIUS_GATHER ? 32 : 1)) {
+        int cbase = 0;
+        if (lane == 0) cbase = atomicAdd(&J.gs->work, 32);
+        cbase = __shfl_sync(SD_FULL, cbase, 0);
+        if (cbase >= g.n) { exhausted = true; break; }
+        const int i = cbase + lane;
+        bool walk = false;
+        if (i < g.n) {
+            const float4 qp = __ldg(J.sp + i);
+            const float qx = qp.x, qy = qp.y, qz = qp.z;
+            if (qx != finf) {                                    // else: removed by the statistical filter (count already 0)
+                walk = true;
+                if (cap >= 0) {
+                    // whole level-1 cells inside the ball: their alive points count without being looked at
+                    const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
+                    const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
+                    const float cell1 = (float)(g.cell * 4.0), qa = pick_axis(ga2, qx, qy, qz);
+                    const float f0 = (float)(q0 - g.o0), f1 = (float)(q1 - g.o1);        // query relative to the grid origin
+                    const int k0 = c0 >> 2, k1 = c1 >> 2;
+                    int sure = 0;
 #pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
+                    for (int dy = -1; dy <= 1; ++dy) {
 #pragma unroll
-                for (int dx = -1; dx <= 1; ++dx) {
-                    const int e0 = k0 + dx, e1 = k1 + dy;
-                    if (e0 < 0 || e0 >= g.d0[1] || e1 < 0 || e1 >= g.d1[1]) continue;
-                    const uint4 bx = __ldg(J.cell_box + e1 * g.d0[1] + e0);
-                    const int na = (int)bx.x;
-                    if (na <= 0) continue;
-                    const float blo = key2f(bx.y), bhi = key2f(bx.z);
-                    const float lo0 = (float)e0 * cell1, lo1 = (float)e1 * cell1;
-                    const float far0 = fmaxf(fabsf(f0 - lo0), fabsf(lo0 + cell1 - f0)) + 1e-4f;
-                    const float far1 = fmaxf(fabsf(f1 - lo1), fabsf(lo1 + cell1 - f1)) + 1e-4f;
-                    const float far2 = fmaxf(fabsf(qa - blo), fabsf(bhi - qa)) + 1e-4f;
-                    if ((far0 * far0 + far1 * far1) + far2 * far2 <= r2_sure) sure += na;
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int e0 = k0 + dx, e1 = k1 + dy;
+                            if (e0 < 0 || e0 >= g.d0[1] || e1 < 0 || e1 >= g.d1[1]) continue;
+                            const uint4 bx = __ldg(J.cell_box + e1 * g.d0[1] + e0);
+                            const int na = (int)bx.x;
+                            if (na <= 0) continue;
+                            const float blo = key2f(bx.y), bhi = key2f(bx.z);
+                            const float lo0 = (float)e0 * cell1, lo1 = (float)e1 * cell1;
+                            const float far0 = fmaxf(fabsf(f0 - lo0), fabsf(lo0 + cell1 - f0)) + 1e-4f;
+                            const float far1 = fmaxf(fabsf(f1 - lo1), fabsf(lo1 + cell1 - f1)) + 1e-4f;
+                            const float far2 = fmaxf(fabsf(qa - blo), fabsf(bhi - qa)) + 1e-4f;
+                            if ((far0 * far0 + far1 * far1) + far2 * far2 <= r2_sure) sure += na;
+                        }
+                    }
+                    if (sure > cap) { J.cnt[__float_as_int(qp.w)] = cap + 1; walk = false; }
                 }
             }
-            if (sure > cap) { J.cnt[__float_as_int(qp.w)] = cap + 1; continue; }
         }
+        const unsigned wm = __ballot_sync(SD_FULL, walk);
+        if (walk) wq[(qhead + qcount + __popc(wm & ((1u << lane) - 1u))) & 63] = i;
+        qcount += __popc(wm);
+        __syncwarp();
+      }
+      if (qcount == 0) break;                                    // nothing waits and nothing is left to claim
+      // ---- phase B: up to 32 waiting queries, one per lane
+      const int take = min(qcount, 32);
+      if (lane < take) {
+        const int i = wq[(qhead + lane) & 63];
+        const float4 qp = __ldg(J.sp + i);
+        const float qx = qp.x, qy = qp.y, qz = qp.z;
+        const double q0 = (double)pick_axis(g.a0, qx, qy, qz), q1 = (double)pick_axis(g.a1, qx, qy, qz);
+        const int c0 = cell_coord(q0, g.o0, g.inv_cell, g.d0[0]), c1 = cell_coord(q1, g.o1, g.inv_cell, g.d1[0]);
         int L = Lmax;
         if (cap >= 0) {
             int s3[3], e3[3];
@@ -1139,8 +1204,10 @@ radius_kernel(const KnnJob* __restrict__ jobs) {
         }
         J.cnt[__float_as_int(qp.w)] = (cap >= 0 && count > cap) ? cap + 1 : count;
       }
+      __syncwarp();
+      qhead = (qhead + take) & 63; qcount -= take;
     }
-    if (lane_id() == 0) {
+    if (lane == 0) {
         __threadfence();
         if (atomicAdd(&J.gs->ticket, 1u) == gridDim.x * (kKnnThreads / 32) - 1) { J.gs->ticket = 0; J.gs->work = 0; }
     }
@@ -1237,7 +1304,7 @@ int sd_launch_radius(const sd::KnnJob* d_jobs, int njobs, int cap, cudaStream_t 
     // statistical filter applied to the sorted copies (if any) + per-cell statistics of what is left
     sor_mark_kernel<<<grid_for(3 * cap, kGridThreads, 4, njobs, 8), kGridThreads, 0, st>>>(d_jobs);
 #ifndef SD_RADIUS_WAVES
-#define SD_RADIUS_WAVES 5      // the resident set, like the k-NN kernel: surplus CTAs of a claim-until-empty kernel only hold slots
+#define SD_RADIUS_WAVES SD_RADIUS_MINB   // the resident set, like the k-NN kernel: surplus CTAs of a claim-until-empty kernel only hold slots
                                // (measured: 16 -> 5 waves, pipelined step +1.8 %)
 #endif
     radius_kernel<<<grid_for(cap, kKnnThreads, 1, njobs, SD_RADIUS_WAVES), kKnnThreads, 0, st>>>(d_jobs);

@@ -91,13 +91,33 @@ compact_kernel(const CompactJob* __restrict__ jobs) {
     __shared__ float s_x[kCompactTile], s_y[kCompactTile], s_z[kCompactTile];
     __shared__ int s_src[kCompactTile];
 
-    const CompactJob J = jobs[blockIdx.y];
-    const int n = *J.n_in;
+#ifndef SD_COMPACT_SMEM
+#define SD_COMPACT_SMEM 1
+#endif
     const int tid = threadIdx.x;
-    const int ntiles = ceil_div(n, kCompactTile);
+#if SD_COMPACT_SMEM
+    // the job descriptor and the resolved predicates are CTA-uniform: in shared memory they cost an LDS where they are used
+    // instead of ~70 registers per thread (16 pointers, two predicates with their fp64 parameters)
+    __shared__ CompactJob s_job;
+    __shared__ PredRt s_pred[2];
+    if (tid == 0) {
+        s_job = jobs[blockIdx.y];
+        s_pred[0] = resolve_pred(s_job.pred);
+        s_pred[1] = s_job.has_pred2 ? resolve_pred(s_job.pred2) : s_pred[0];
+    }
+    __syncthreads();
+    const CompactJob& J = s_job;
+    const PredRt& P = s_pred[0];
+    const PredRt& P2 = s_pred[1];
+    const bool two = J.has_pred2 != 0;
+#else
+    const CompactJob J = jobs[blockIdx.y];
     const PredRt P = resolve_pred(J.pred);
     const bool two = J.has_pred2 != 0;
     const PredRt P2 = two ? resolve_pred(J.pred2) : P;
+#endif
+    const int n = *J.n_in;
+    const int ntiles = ceil_div(n, kCompactTile);
     const uint8_t* __restrict__ flag = J.flag;
     int mid_local = 0;
     const float* __restrict__ X = J.x; const float* __restrict__ Y = J.y; const float* __restrict__ Z = J.z;

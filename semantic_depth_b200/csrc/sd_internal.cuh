@@ -18,7 +18,10 @@ constexpr int kCompactThreads = 256;
 constexpr int kCompactItems = SD_COMPACT_ITEMS;
 constexpr int kCompactTile = kCompactThreads * kCompactItems;   // 2048 points per tile
 constexpr int kScanTile = 4096;                                 // cell-count scan tile
-constexpr int kPlaneBlocks = 64;                                // partial-sum blocks per plane job
+#ifndef SD_PLANE_BLOCKS
+#define SD_PLANE_BLOCKS 64
+#endif
+constexpr int kPlaneBlocks = SD_PLANE_BLOCKS;                   // partial-sum blocks per plane job
 constexpr int kPlaneSums = 9;
 constexpr int kMaxKnnK = 64;
 #ifndef SD_KNN_LEVELS

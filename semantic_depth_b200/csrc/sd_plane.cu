@@ -44,25 +44,46 @@ plane_moments_kernel(const PlaneJob* __restrict__ jobs) {
     double s[kPlaneSums];
 #pragma unroll
     for (int k = 0; k < kPlaneSums; ++k) s[k] = 0.0;
-    for (int i = blockIdx.x * kPlaneThreads + tid; i < n; i += gridDim.x * kPlaneThreads) {
-        bool alive = flag ? (flag[i] != 0) : true;
-        if (marking) {
-            const float ad = fabsf(__ldg(J.mark.col + i) - mk_med);            // pcl.py:79
-            const float pen = (0.6745f * ad) / mk_mad;                          // pcl.py:63
-            alive = alive && (pen < J.mark.thr);                                // pcl.py:67
-            J.flag_out[i] = alive ? 1 : 0;
+#ifndef SD_PLANE_ILP
+#define SD_PLANE_ILP 1
+#endif
+    // SD_PLANE_ILP rows per trip, their loads issued together (the loop is bound by load latency, not by its fp64 work); the rows
+    // of a trip are accumulated in ascending order, so the sums do not depend on the unroll factor
+    constexpr int ILP = SD_PLANE_ILP;
+    const int stride = gridDim.x * kPlaneThreads;
+    for (int i0 = blockIdx.x * kPlaneThreads + tid; i0 < n; i0 += stride * ILP) {
+        bool alive[ILP]; float px[ILP], py[ILP], pz[ILP], mc[ILP];
+#pragma unroll
+        for (int r = 0; r < ILP; ++r) {
+            const int i = i0 + r * stride;
+            const bool in = i < n;
+            const int ic = in ? i : i0;
+            alive[r] = in && (flag ? (flag[ic] != 0) : true);
+            mc[r] = marking ? __ldg(J.mark.col + ic) : 0.f;
+            px[r] = __ldg(J.x + ic); py[r] = __ldg(J.y + ic); pz[r] = __ldg(J.z + ic);
         }
-        if (!alive) continue;
-        float u, v, w;
-        pick_uvw(J.axis, __ldg(J.x + i), __ldg(J.y + i), __ldg(J.z + i), u, v, w);
-        if (J.use_inliers) {
-            double a = ((h0 * (double)u + h1 * (double)v) - (double)w) + h2;
-            if (!(fabs(a) < J.thr)) continue;
+#pragma unroll
+        for (int r = 0; r < ILP; ++r) {
+            const int i = i0 + r * stride;
+            if (i >= n) continue;
+            if (marking) {
+                const float ad = fabsf(mc[r] - mk_med);                            // pcl.py:79
+                const float pen = (0.6745f * ad) / mk_mad;                          // pcl.py:63
+                alive[r] = alive[r] && (pen < J.mark.thr);                          // pcl.py:67
+                J.flag_out[i] = alive[r] ? 1 : 0;
+            }
+            if (!alive[r]) continue;
+            float u, v, w;
+            pick_uvw(J.axis, px[r], py[r], pz[r], u, v, w);
+            if (J.use_inliers) {
+                double a = ((h0 * (double)u + h1 * (double)v) - (double)w) + h2;
+                if (!(fabs(a) < J.thr)) continue;
+            }
+            const double du = (double)u - (double)u0, dv = (double)v - (double)v0, dw = (double)w - (double)w0;
+            s[0] += du * du; s[1] += du * dv; s[2] += du;
+            s[3] += dv * dv; s[4] += dv;      s[5] += du * dw;
+            s[6] += dv * dw; s[7] += dw;      s[8] += 1.0;
         }
-        const double du = (double)u - (double)u0, dv = (double)v - (double)v0, dw = (double)w - (double)w0;
-        s[0] += du * du; s[1] += du * dv; s[2] += du;
-        s[3] += dv * dv; s[4] += dv;      s[5] += du * dw;
-        s[6] += dv * dw; s[7] += dw;      s[8] += 1.0;
     }
 #pragma unroll
     for (int k = 0; k < kPlaneSums; ++k) s[k] = warp_sum(s[k]);

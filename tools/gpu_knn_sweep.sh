@@ -16,7 +16,7 @@ for spec in ${SWEEP}; do
 import json
 try:
     d = json.loads(open('gpurun_out/sweep_${name}_$cs.json').read().strip().splitlines()[-1])
-    print('== $name cs=$cs: %.1f frames/s  knn alone %.4f ms  ror %.4f ms  stages sum %.4f ms  mismatches %d golden %s' % (d['value'], d['stage_ms']['road_knn'], d['stage_ms']['road_ror'], d['stage_ms']['sum'], d['result_mismatches_vs_first_pass'], (d.get('golden_check_batch0') or {}).get('all_stage_counts_equal')))
+    print('== $name cs=$cs: %.1f frames/s  knn alone %.4f ms  ror %.4f ms  plane %.4f fences %.4f mad %.4f  stages sum %.4f ms  mismatches %d golden %s' % (d['value'], d['stage_ms']['road_knn'], d['stage_ms']['road_ror'], d['stage_ms']['road_plane'], d['stage_ms']['fences'], d['stage_ms']['road_mad'], d['stage_ms']['sum'], d['result_mismatches_vs_first_pass'], (d.get('golden_check_batch0') or {}).get('all_stage_counts_equal')))
 except Exception as e:
     print('== $name cs=$cs failed', e)
 PY

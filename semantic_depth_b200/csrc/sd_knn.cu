@@ -421,6 +421,17 @@ __device__ __forceinline__ double dist2_f64(const KnnJob& J, int j, float qx, fl
 #define SD_KNN_BATCH 4
 #endif
 constexpr int kBatch = SD_KNN_BATCH;             // candidates whose loads are issued together (the loops are latency-bound)
+#ifndef SD_KNN_PREFETCH
+#define SD_KNN_PREFETCH 0   // bit 0: the bound phase's windows, bit 1: the collect phase's row runs are prefetched into L1 line by line
+                            // before the first dependent load (memory-level parallelism instead of one miss after the other)
+#endif
+// prefetch the cache lines of sorted-copy entries [s, e) (16 bytes each)
+__device__ __forceinline__ void prefetch_run(const float4* sp, int s, int e) {
+    const char* p = reinterpret_cast<const char*>(sp + s);
+    const char* const end = reinterpret_cast<const char*>(sp + e);
+    for (p = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127); p < end; p += 128)
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
 
 // visit the cells that square(r) adds to square(rold) (rold < 0: everything) at one level, row by row
 template <typename F>
@@ -594,6 +605,10 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
             }
             const int n0 = we[0] - ws[0], n1 = we[1] - ws[1], n2 = we[2] - ws[2];
             fed = n0 + n1 + n2;
+            if (SD_KNN_PREFETCH & 1) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) prefetch_run(J.sp, ws[t], we[t]);
+            }
             for (int t0 = 0; t0 < fed; t0 += kBatch) {            // flattened over the three windows, kBatch loads in flight
                 float4 c[kBatch];
 #pragma unroll
@@ -663,6 +678,9 @@ knn_kernel(const KnnJob* __restrict__ jobs) {
                     // that ends beyond row kListCap means "more than kListCap hits" (rows kListCap, kListCap + 1 are spare)
                     uint16_t* const lbase = &s_list[0][tid];
                     int lp = 0;                                              // element offset of the next entry
+                    if (SD_KNN_PREFETCH & 2) {
+                        for (int ri = 0; ri < nruns; ++ri) { const int2 se = s_seg[ri][tid]; prefetch_run(J.sp, se.x, se.y); }
+                    }
                     constexpr int lp_max = (kListCap + 1) * kKnnThreads;
                     for (int ri = 0; ri < nruns; ++ri) {
                         const int2 se = s_seg[ri][tid];

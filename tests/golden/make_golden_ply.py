@@ -11,7 +11,6 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-sys.path.insert(0, "/root/reference")
 from oracle import ply_ref  # noqa: E402
 
 
@@ -37,6 +36,7 @@ def make_cloud(seed, n, dtype, genuine64=False):
 
 
 def main():
+    sys.path.insert(0, "/root/reference")                                    # only here: tests import make_cloud from this module
     from semantic_depth_lib.point_cloud_2_ply import PointCloud2Ply          # the reference's class, unmodified
     out = {}
     for i, (n, dtype, genuine64) in enumerate([(1000, np.float32, False), (50_000, np.float32, False), (3000, np.float64, False),

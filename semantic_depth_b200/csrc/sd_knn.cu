@@ -884,14 +884,25 @@ __device__ __forceinline__ void heavy_for_cells(const KnnJob& J, const GridRt& g
     }
 }
 
+#ifndef SD_KNN_HEAVY_MINB
+#define SD_KNN_HEAVY_MINB 6   // resident CTAs per SM the register allocation is bounded for: 80 registers, the launch (6 CTAs per SM) is one wave
+                              // (measured: 3 143-3 155 frames/s against 3 140-3 142 unbounded at 112 registers)
+#endif
 template <int KS>
-__global__ void __launch_bounds__(kHeavyWarps * 32)
+__global__ void __launch_bounds__(kHeavyWarps * 32, (KS <= 11 ? SD_KNN_HEAVY_MINB : 1))
 knn_heavy_kernel(const KnnJob* __restrict__ jobs) {
     constexpr int K = KS - 1;
     constexpr int KN = K > 0 ? K : 1;
     __shared__ int s_hl[kHeavyWarps][kHeavyList];
     const KnnJob J = jobs[blockIdx.y];
+#if SD_KNN_GRID_SMEM
+    __shared__ GridRt s_grid;
+    if (threadIdx.x == 0) s_grid = load_grid(J.gs);
+    __syncthreads();
+    const GridRt& g = s_grid;
+#else
     const GridRt g = load_grid(J.gs);
+#endif
     const int keff = min(J.k, g.n);
     const int ga2 = J.gs->a2;
     const int w = warp_id(), lane = lane_id();
@@ -1270,7 +1281,10 @@ static int launch_knn_t(const sd::KnnJob* d_jobs, dim3 grid, cudaStream_t st) {
         configured = true;
     }
     knn_kernel<KS><<<grid, kKnnThreads, smem, st>>>(d_jobs);
-    knn_heavy_kernel<KS><<<dim3(max(1u, min(grid.x, (148u * 6u) / grid.y)), grid.y), kHeavyWarps * 32, 0, st>>>(d_jobs);
+#ifndef SD_KNN_HEAVY_WAVES
+#define SD_KNN_HEAVY_WAVES 6
+#endif
+    knn_heavy_kernel<KS><<<dim3(max(1u, min(grid.x, (148u * SD_KNN_HEAVY_WAVES) / grid.y)), grid.y), kHeavyWarps * 32, 0, st>>>(d_jobs);
     SD_LAUNCH_CHECK();
     return SD_OK;
 }

@@ -141,6 +141,34 @@ def load() -> C.CDLL:
     return lib
 
 
+OPS_PATH = os.path.join(os.path.dirname(LIB_PATH), "libsd_torch_ops.so")
+_ops = None
+
+
+def load_ops():
+    """The TORCH_LIBRARY op layer over the C ABI (csrc/sd_torch_ops.cpp): ``torch.ops.sd_fusion``.  It validates device,
+    dtype and contiguity of every tensor in C++ (RuntimeError) and forwards to sd_fuse_frames / sd_fuse_frames_scores."""
+    global _ops
+    if _ops is not None:
+        return _ops
+    import torch
+    load()                                   # the C ABI library first: same checks, same error if it is missing
+    if not os.path.exists(OPS_PATH):
+        raise SdError(f"{OPS_PATH} not found: build it with `python -m semantic_depth_b200.build`")
+    torch.ops.load_library(OPS_PATH)
+    ops = torch.ops.sd_fusion
+    if int(ops.abi_version()) != 2 or int(ops.result_bytes()) != C.sizeof(SdFrameResult):
+        raise SdError("libsd_torch_ops.so does not match libsd_fusion.so / the ctypes structs")
+    _ops = ops
+    return ops
+
+
+def struct_tensor(st):
+    """A ctypes struct of the ABI as the CPU uint8 tensor the op layer takes."""
+    import torch
+    return torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8)
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != SD_OK:
         msg = load().sd_last_error()

@@ -14,6 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsd_fusion.so")
+OPS_LIB = os.path.join(HERE, "libsd_torch_ops.so")       # TORCH_LIBRARY op layer over the C ABI (host C++ only)
+OPS_SRC = os.path.join(CSRC, "sd_torch_ops.cpp")
 SOURCES = ["sd_api.cu", "sd_pixel.cu", "sd_select.cu", "sd_compact.cu", "sd_plane.cu", "sd_knn.cu", "sd_ransac.cu", "sd_resize.cu", "sd_ply.cu", "sd_overlay.cu", "sd_fcn_head.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -27,9 +29,9 @@ def _nvcc() -> str:
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(OPS_LIB):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(OPS_LIB))
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sd_fusion.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
@@ -62,7 +64,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
+    build_ops(verbose)
     return LIB
+
+
+def build_ops(verbose: bool = False) -> str:
+    """libsd_torch_ops.so: csrc/sd_torch_ops.cpp against this interpreter's PyTorch, linked to libsd_fusion.so next to it."""
+    import torch
+    from torch.utils.cpp_extension import include_paths, library_paths
+    cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           "-I", os.path.join(HERE, "..", "include"), "-I", cuda_inc]
+    for inc in include_paths():
+        cmd += ["-isystem", inc]
+    cmd += [OPS_SRC, "-o", OPS_LIB]
+    for lp in library_paths():
+        cmd += ["-L", lp, f"-Wl,-rpath,{lp}"]
+    cmd += ["-L", HERE, "-lsd_fusion", "-Wl,-rpath,$ORIGIN", "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda", "-ltorch"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 or verbose:
+        sys.stderr.write(f"--- {' '.join(cmd)}\n{r.stdout}\n")
+    if r.returncode != 0:
+        raise RuntimeError("building libsd_torch_ops.so failed")
+    return OPS_LIB
 
 
 if __name__ == "__main__":

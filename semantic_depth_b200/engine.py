@@ -166,9 +166,10 @@ class FusionEngine:
                         raise TypeError("hypotheses must be contiguous CUDA int32 [B,K,3]")
                     n_hyp = h.shape[1]
             self._hyp_keepalive = (hr, hl, hg)
-        check(self.lib.sd_fuse_frames(_ptr(logits), _ptr(disp), b, self.height, self.width, C.byref(cam), C.byref(ps),
-                                      _ptr(hr), _ptr(hl), _ptr(hg), n_hyp, _ptr(self._results), self._ws, _stream_ptr()),
-              "sd_fuse_frames")
+        # through the TORCH_LIBRARY op layer (csrc/sd_torch_ops.cpp): device / dtype / contiguity are checked again in C++,
+        # the stream is the one PyTorch uses on the tensors' device
+        _lib.load_ops().fuse_frames(logits, disp, _lib.struct_tensor(cam), _lib.struct_tensor(ps), hr, hl, hg,
+                                    int(self._ws.value), self._results)
         return b
 
     def fetch(self, batch: int) -> FusionResult:
@@ -345,9 +346,8 @@ class FusionEngine:
         sc, upw, upb = scores.contiguous(), weights.contiguous(), bias.contiguous()
         b = self._check_scores(sc, upw, upb, disp)
         cam, ps = camera_struct(intr), params_struct(params)
-        check(self.lib.sd_fuse_frames_scores(_ptr(sc), _ptr(upw), _ptr(upb), _ptr(disp), b, self.height, self.width,
-                                             C.byref(cam), C.byref(ps), _ptr(self._results), self._ws, _stream_ptr()),
-              "sd_fuse_frames_scores")
+        _lib.load_ops().fuse_frames_scores(sc, upw, upb, disp, _lib.struct_tensor(cam), _lib.struct_tensor(ps),
+                                           int(self._ws.value), self._results)
         return b
 
     # ------------------------------------------------------------------------------------------

@@ -240,3 +240,20 @@ def test_host_placement_logic_on_cpu():
     # one rank, or as many ranks as GPUs: the plain map, nothing is measured
     dev, rep = h.choose_device(0, 1)
     assert dev == 0 and rep["map"] == "first"
+
+
+def test_torch_op_layer_loads_and_rejects_host_tensors():
+    """the TORCH_LIBRARY layer over the C ABI checks device / dtype / contiguity in C++ and raises RuntimeError."""
+    import ctypes as C
+    import torch
+    from semantic_depth_b200 import _lib
+    ops = _lib.load_ops()
+    assert int(ops.abi_version()) == 2 and int(ops.result_bytes()) == C.sizeof(_lib.SdFrameResult)
+    cam = _lib.struct_tensor(_lib.SdCamera())
+    ps = _lib.struct_tensor(_lib.SdParams())
+    assert cam.numel() == C.sizeof(_lib.SdCamera) and ps.numel() == C.sizeof(_lib.SdParams)
+    res = torch.zeros(C.sizeof(_lib.SdFrameResult), dtype=torch.uint8)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ops.fuse_frames(torch.zeros(1, 8, 3), torch.zeros(1, 2, 2, 4), cam, ps, None, None, None, 1, res)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ops.fuse_frames_scores(torch.zeros(1, 1, 1, 3), torch.zeros(16, 16, 3, 3), torch.zeros(3), torch.zeros(1, 2, 8, 8), cam, ps, 1, res)

@@ -255,3 +255,39 @@ def test_fused_randomised_sweep(cuda_device):
             o = frame_ref.fuse_frame(logits, disp, intr.as_q32(), intr.disparity_mult, P)
             check_against_oracle(res, f, o, eng)
         eng.close()
+
+
+def test_torch_op_layer_checks_its_arguments(cuda_device):
+    """torch.ops.sd_fusion.fuse_frames validates device / dtype / contiguity / shapes in C++ (RuntimeError) and is
+    the path FusionEngine.enqueue takes (its answers are the oracle's in every other test of this file)."""
+    import ctypes as C
+    from semantic_depth_b200 import _lib
+    from semantic_depth_b200.engine import camera_struct, params_struct
+    h, w = 64, 128
+    logits, disp, intr = scene.make_batch(1, h, w, first_seed=0)
+    eng = FusionEngine(h, w, max_frames=1)
+    ops = _lib.load_ops()
+    lg, dp = torch.from_numpy(logits).cuda(), torch.from_numpy(disp).cuda()
+    cam, ps = _lib.struct_tensor(camera_struct(intr)), _lib.struct_tensor(params_struct(FusionParams()))
+    ws, res = int(eng._ws.value), eng._results
+
+    def call(lg_=lg, dp_=dp, cam_=cam, ps_=ps, ws_=ws, res_=res, hyp=None):
+        ops.fuse_frames(lg_, dp_, cam_, ps_, hyp, None, None, ws_, res_)
+
+    call()                                                                        # the good call
+    want = eng.fetch(1)
+    ref = eng.fuse_frames(lg, dp, intr, FusionParams())
+    assert want.raw.tobytes() == ref.raw.tobytes() and want.counts(0)["road_gather"] > 0       # the same answers, byte for byte
+    for bad, pattern in [(dict(lg_=lg.double()), "must be Float"), (dict(lg_=lg.cpu()), "CUDA tensor"),
+                         (dict(lg_=lg.transpose(1, 2)), "contiguous|must be"), (dict(dp_=dp[:, :, :, ::2]), "contiguous"),
+                         (dict(dp_=dp.reshape(1, 2, w, h).contiguous()[:, :1]), r"\[B, 2, H, W\]"),
+                         (dict(lg_=lg[:, :-1].contiguous()), "pixels"), (dict(cam_=cam[:-1].clone()), "bytes"),
+                         (dict(ps_=ps.cuda()), "CPU uint8"), (dict(ws_=0), "null workspace"), (dict(res_=res[:8]), "bytes"),
+                         (dict(res_=res.cpu()), "CUDA tensor"), (dict(hyp=torch.zeros(1, 4, 3, device="cuda")), "must be Int")]:
+        with pytest.raises(RuntimeError, match=pattern):
+            call(**bad)
+    # the library's own refusals surface as RuntimeError with its message (a 2-frame batch into a 1-frame workspace)
+    lg2, dp2 = lg.repeat(2, 1, 1), dp.repeat(2, 1, 1, 1)
+    res2 = torch.zeros(2 * C.sizeof(_lib.SdFrameResult), dtype=torch.uint8, device="cuda")
+    with pytest.raises(RuntimeError, match="sd_fuse_frames failed"):
+        ops.fuse_frames(lg2, dp2, cam, ps, None, None, None, ws, res2)
